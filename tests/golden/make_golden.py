@@ -1,0 +1,46 @@
+"""Regenerates tests/golden/*.npz from the oracle (run from the repo root: python tests/golden/make_golden.py).
+
+The reference repository has no golden vectors (it has no code: /root/reference/README.md:1-3), so
+these fixtures are outputs of the oracle on the canonical synthetic weights; they freeze the
+oracle's behaviour (tests/test_golden.py, CPU) and are what the CUDA path is compared against on
+the GPU box (tests/test_gpu_parity.py), where the oracle is also re-run live.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import synthetic  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+FORWARD_CASE = dict(B=2, S=12, T=20, data_seed=201, seed=7, stop_bias=-8.0)
+INFER_CASE = dict(B=3, S=16, max_len=48, data_seed=202, seed=7, stop_bias=-0.45)
+
+
+def main():
+    torch.set_num_threads(1)
+    c = FORWARD_CASE
+    m = synthetic.make_model(stop_bias=c["stop_bias"])
+    digest = synthetic.state_dict_digest(m.state_dict())
+    ph, pl, mels, ml = synthetic.make_inputs(c["B"], c["S"], c["T"], c["data_seed"], ragged=True)
+    with torch.no_grad():
+        mb, ma, st = m(ph, pl, mels, ml, seed=c["seed"])
+        mem = m.encode(ph, pl)
+    np.savez_compressed(os.path.join(HERE, "forward_small.npz"), digest=np.array(digest),
+                        phonemes=ph.numpy(), phoneme_lens=pl.numpy(), mels=mels.numpy(), mel_lens=ml.numpy(),
+                        memory=mem.numpy(), mel_before=mb.numpy(), mel_after=ma.numpy(), stop_logits=st.numpy())
+    c = INFER_CASE
+    m = synthetic.make_model(stop_bias=c["stop_bias"])
+    ph, pl, _, _ = synthetic.make_inputs(c["B"], c["S"], 8, c["data_seed"], ragged=True)
+    ma, lens, st, mb = m.inference(ph, pl, max_len=c["max_len"], seed=c["seed"], return_before=True)
+    np.savez_compressed(os.path.join(HERE, "inference_small.npz"),
+                        phonemes=ph.numpy(), phoneme_lens=pl.numpy(), mel_after=ma.numpy(), mel_before=mb.numpy(),
+                        mel_lens=lens.numpy(), stop_logits=st.numpy())
+    print("digest", digest, "lens", lens.tolist())
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,120 @@
+/* tts_b200.h -- C ABI of libtts_b200.so: the B200-native (sm_100a) Transformer-TTS hot path.
+ *
+ * What this boundary replaces.  The reference repository (keonlee9420/Transformer-tacotron2)
+ * ships NO code -- /root/reference/README.md:1-3 is its whole content (title, one sentence and
+ * the link to Li et al., AAAI 2019 at README.md:3).  BASELINE.json `north_star` therefore defines
+ * the interface to keep as a torch.nn.Module:
+ *
+ *     TransformerTTS.forward(phonemes, phoneme_lens, mels, mel_lens)   -> mel_before, mel_after, stop_logits
+ *     TransformerTTS.inference(phonemes, phoneme_lens, max_len, seed)  -> mel_after, mel_lens, stop_logits
+ *
+ * (restated executable in oracle/transformer_tts.py:TransformerTTS).  The entry
+ * points below are exactly what a Python binding of those two methods calls (the ctypes stub is in
+ * INTEGRATION.md and, live, in transformer_tacotron2_b200/_lib.py).  Each declaration cites the
+ * interface it stands behind.
+ *
+ * Conventions: plain C types only; raw DEVICE pointers + explicit sizes + a cudaStream_t passed as
+ * void*; the caller owns every buffer including the workspace (sized by tts_workspace_bytes); the
+ * handle owns only the packed weights.  All work is enqueued on the caller's stream; calls marked
+ * [sync] synchronise that stream.  Return value: 0 = ok, < 0 = argument error (TTS_E_*),
+ * > 0 = cudaError_t.  tts_last_error_string() gives detail.  A handle is bound to one device and is
+ * not thread-safe.  There is no CPU fallback: without an sm_100 device tts_create fails.
+ */
+#ifndef TTS_B200_H_
+#define TTS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTS_E_ARG (-1)       /* bad argument / shape */
+#define TTS_E_STATE (-2)     /* call order (weights not finalised, decode not begun, ...) */
+#define TTS_E_WEIGHT (-3)    /* unknown / missing / mis-sized weight */
+#define TTS_E_DEVICE (-4)    /* no sm_100 device */
+
+typedef struct TtsHandle TtsHandle;
+
+/* oracle/transformer_tts.py:TTSConfig (SURVEY.md section 5 "Config / flags").  Only the base model
+ * (d_model 512, 8 heads, d_ff 2048, 80 mels, prenet 256, kernel 5) is accepted. */
+typedef struct TtsConfig {
+    uint32_t struct_size;
+    int32_t n_vocab, d_model, n_heads, n_enc_layers, n_dec_layers, d_ff, n_mels, d_prenet;
+    int32_t enc_conv_layers, conv_kernel, postnet_channels, postnet_layers, max_pos;
+    float ln_eps, bn_eps;
+} TtsConfig;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* TransformerTTS.__init__ (oracle/transformer_tts.py:TransformerTTS.__init__). */
+int tts_create(const TtsConfig* cfg, int device, TtsHandle** out);
+int tts_destroy(TtsHandle* h);
+const char* tts_last_error_string(TtsHandle* h);
+/* Library / build identification ("tts_b200 <version> sm_100a"). */
+const char* tts_version(void);
+
+/* ---- weights: nn.Module.load_state_dict (same keys as the oracle's state_dict) --------------- */
+/* Stage one fp32 tensor (HOST pointer, `numel` elements, C-contiguous) under its state_dict key. */
+int tts_load_weight(TtsHandle* h, const char* name, const float* host_data, int64_t numel);
+/* Pack everything staged so far: bf16 cast, BatchNorm folded into the convs (P5), Q/K/V and
+ * [mel|stop] concatenated, decode-step weights swizzled into MMA fragment order; uploads. [sync] */
+int tts_finalize_weights(TtsHandle* h);
+
+/* ---- options ---------------------------------------------------------------------------------- */
+/* "decode_persistent": 1 (default) one cooperative persistent kernel for the AR loop; 0 one launch per phase. */
+int tts_set_option(TtsHandle* h, const char* key, int64_t value);
+
+/* ---- workspace ---------------------------------------------------------------------------------- */
+/* Bytes of caller-owned device scratch (KV caches, activations) for batch B, S phonemes, T frames. */
+size_t tts_workspace_bytes(TtsHandle* h, int B, int S, int T);
+
+/* ---- TransformerTTS.inference (oracle/transformer_tts.py:TransformerTTS.inference) ---------- */
+/* Encoder + hoisted cross-K/V projection.  phonemes [B][S] int64, phoneme_lens [B] int32 (device).
+ * T = the frame count the workspace was sized for (max_len of the decode that follows).
+ * memory_out: optional fp32 [B][S][512] copy of the encoder output (may be NULL). */
+int tts_encode(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* phoneme_lens,
+               int B, int S, int T, float* memory_out, void* stream);
+/* Reset the AR state (KV cache cursor, lengths, stop flags).  utt_offset = global id of utterance 0
+ * (dropout masks are keyed by global utterance id so a sharded batch reproduces the unsharded one). */
+int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_len, uint64_t seed, int utt_offset, void* stream);
+/* Run up to n_steps decoder steps (stops early, on the device, once every utterance has fired). */
+int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* stream);
+/* [sync] steps completed so far and number of finished utterances. */
+int tts_decode_status(TtsHandle* h, void* ws, int* t_done, int* n_finished, void* stream);
+/* Mask past the stop frame, run the postnet, add the residual.  T_out = t_done.  Outputs (device):
+ * mel_after [B][T_out][80] f32, mel_lens [B] i32, stop_logits [B][T_out] f32, mel_before (optional). */
+int tts_decode_end(TtsHandle* h, void* ws, int T_out, float* mel_after, int32_t* mel_lens,
+                   float* stop_logits, float* mel_before, void* stream);
+/* The whole of .inference() with HOST buffers (pageable or pinned): H2D, encode, decode loop,
+ * postnet, D2H.  Outputs are written compactly as [B][T_out]...; *T_out returns the frames run.
+ * `ws` is device scratch of tts_workspace_bytes(B, S, max_len). [sync] */
+int tts_infer_host(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* phoneme_lens, int B, int S,
+                   int max_len, uint64_t seed, int utt_offset, float* mel_after, int32_t* mel_lens,
+                   float* stop_logits, int* T_out, void* stream);
+
+/* ---- TransformerTTS.forward, eval mode (oracle/transformer_tts.py:TransformerTTS.forward) --- */
+/* Teacher-forced forward.  Device pointers: phonemes [B][S] i64, lens i32, mels [B][T][80] f32,
+ * outputs mel_before / mel_after [B][T][80] f32 and stop_logits [B][T] f32 (zero past mel_lens). */
+int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* phoneme_lens,
+                const float* mels, const int32_t* mel_lens, int B, int S, int T, uint64_t seed, int utt_offset,
+                float* mel_before, float* mel_after, float* stop_logits, void* stream);
+
+/* ---- per-kernel entry points (tests/test_gpu_kernels.py; not part of the drop-in surface) ---- */
+/* C[M][N] = act(A[M][K] . W[N][K]^T + bias) ; bf16 in, fp32 out; act 0 none / 1 relu / 2 tanh. */
+int tts_k_gemm(const void* A_bf16, const void* W_bf16, const float* bias, float* C, int M, int N, int K, int act, void* stream);
+/* conv1d(k=5, pad=2) over [B][T][Cin] with W [5][Cout][Cin] bf16 -> fp32 [B][T][Cout]; rows t >= lens[b] zeroed. */
+int tts_k_conv5(const void* X_bf16, const void* W_bf16, const float* bias, const int32_t* lens, float* Y,
+                int B, int T, int Cin, int Cout, int act, void* stream);
+/* Attention core: Q [B][Lq][H*64], K/V [B][Lk][H*64] bf16 -> O [B][Lq][H*64] bf16. */
+int tts_k_attention(const void* Q, const void* K, const void* V, void* O, const int32_t* klens,
+                    int B, int H, int Lq, int Lk, int causal, void* stream);
+/* LayerNorm over rows of 512: fp32 in -> bf16 out. */
+int tts_k_layernorm(const float* X, const float* gamma, const float* beta, void* Y_bf16, int M, float eps, void* stream);
+/* Keep-bits of a p = 0.5 dropout site: out[t][b][c] (uint8) for t < T, b < B, c < C. */
+int tts_k_philox_bits(uint64_t seed, int site, int T, int B, int C, int utt_offset, uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTS_B200_H_ */

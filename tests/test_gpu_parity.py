@@ -1,0 +1,152 @@
+"""T4: end-to-end parity of the CUDA path (through the C ABI) against the oracle run live on the same
+seeded inputs, and against the committed golden fixtures.  pytest -m gpu on a B200.
+
+Tolerances (P15: bf16 operands, fp32 accumulation/statistics/softmax; oracle fp32 throughout):
+  teacher-forced forward : rel-L2 <= 2e-2 on mel_before / mel_after, max-abs <= 5e-2 on stop logits
+  free-running AR        : rel-L2 <= 3e-2 on mel_after over the common frames; mel_lens / stop
+                           indices BIT-EXACT whenever the oracle's stop margin exceeds 10x the
+                           observed logit error (asserted and printed)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.gpu_util import make_b200_model, rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+TOL_MEL = 2e-2
+TOL_STOP = 5e-2
+TOL_AR = 3e-2
+
+
+@pytest.fixture(scope="module")
+def models():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from oracle import synthetic
+    o = synthetic.make_model(stop_bias=-8.0)
+    os_ = synthetic.make_model(stop_bias=-0.45)
+    return o, make_b200_model(o), os_, make_b200_model(os_)
+
+
+def test_encoder_memory(models):
+    from oracle import synthetic
+    o, g, _, _ = models
+    ph, pl, _, _ = synthetic.make_inputs(3, 50, 8, 31, ragged=True)
+    with torch.no_grad():
+        want = o.encode(ph, pl)
+    got = g.encode(ph, pl).cpu()
+    for b in range(3):
+        L = int(pl[b])
+        assert rel_l2(got[b, :L], want[b, :L]) < TOL_MEL
+
+
+@pytest.mark.parametrize("B,S,T,seed", [(2, 12, 20, 201), (4, 100, 400, 101), (3, 37, 129, 33)])
+def test_forward_vs_oracle(models, B, S, T, seed):
+    from oracle import synthetic
+    o, g, _, _ = models
+    ph, pl, mels, ml = synthetic.make_inputs(B, S, T, seed, ragged=True)
+    with torch.no_grad():
+        mb, ma, st = o(ph, pl, mels, ml, seed=7)
+    gb, ga, gs = (t.cpu() for t in g(ph, pl, mels, ml, seed=7))
+    print("forward rel-L2", rel_l2(gb, mb), rel_l2(ga, ma), "stop max-abs", float((gs - st).abs().max()))
+    assert rel_l2(gb, mb) < TOL_MEL and rel_l2(ga, ma) < TOL_MEL
+    assert float((gs - st).abs().max()) < TOL_STOP
+    tm = torch.arange(T)[None, :] >= ml[:, None]
+    assert (gb[tm] == 0).all() and (ga[tm] == 0).all() and (gs[tm] == 0).all()
+
+
+def test_forward_vs_golden(models):
+    o, g, _, _ = models
+    z = np.load(os.path.join(GOLD, "forward_small.npz"))
+    gb, ga, gs = (t.cpu() for t in g(torch.from_numpy(z["phonemes"]), torch.from_numpy(z["phoneme_lens"]),
+                                     torch.from_numpy(z["mels"]), torch.from_numpy(z["mel_lens"]), seed=7))
+    assert rel_l2(gb, torch.from_numpy(z["mel_before"])) < TOL_MEL
+    assert rel_l2(ga, torch.from_numpy(z["mel_after"])) < TOL_MEL
+    assert float((gs - torch.from_numpy(z["stop_logits"])).abs().max()) < TOL_STOP
+
+
+def _compare_inference(o, g, ph, pl, max_len, seed, device_inputs):
+    ma, lens, st, mb = o.inference(ph, pl, max_len=max_len, seed=seed, return_before=True)
+    if device_inputs:
+        ga, gl, gs = (t.cpu() for t in g.inference(ph.cuda(), pl.cuda(), max_len=max_len, seed=seed))
+    else:
+        ga, gl, gs = g.inference(ph, pl, max_len=max_len, seed=seed)
+    B = ph.shape[0]
+    T = min(ga.shape[1], ma.shape[1])
+    # stop margin of the oracle trajectory vs observed logit error on the common, valid frames
+    valid = torch.arange(T)[None, :] < torch.minimum(lens, gl)[:, None]
+    err = float(((gs[:, :T] - st[:, :T]).abs() * valid).max())
+    margin = float(st[:, :T].abs()[valid].min())
+    print(f"AR: lens oracle {lens.tolist()} gpu {gl.tolist()} stop-logit err {err:.4f} margin {margin:.4f} "
+          f"mel rel-L2 {rel_l2(ga[:, :T] * valid[..., None], ma[:, :T] * valid[..., None]):.4f}")
+    return ma, lens, st, ga, gl, gs, err, margin, valid, T
+
+
+@pytest.mark.parametrize("device_inputs", [False, True])
+def test_inference_never_stopping(models, device_inputs):
+    from oracle import synthetic
+    o, g, _, _ = models
+    ph, pl, _, _ = synthetic.make_inputs(3, 30, 8, 41, ragged=True)
+    ma, lens, st, ga, gl, gs, err, margin, valid, T = _compare_inference(o, g, ph, pl, 40, 7, device_inputs)
+    assert gl.tolist() == lens.tolist() == [40, 40, 40]
+    assert ga.shape == ma.shape
+    assert rel_l2(ga, ma) < TOL_AR
+    assert err < TOL_STOP
+
+
+def test_inference_stopping_vs_oracle_and_golden(models):
+    _, _, o, g = models
+    z = np.load(os.path.join(GOLD, "inference_small.npz"))
+    ph, pl = torch.from_numpy(z["phonemes"]), torch.from_numpy(z["phoneme_lens"])
+    ma, lens, st, ga, gl, gs, err, margin, valid, T = _compare_inference(o, g, ph, pl, 48, 7, False)
+    assert lens.tolist() == z["mel_lens"].tolist()
+    assert err < TOL_STOP
+    if margin > 10 * err:
+        assert gl.tolist() == lens.tolist()            # stop indices / lengths bit-exact
+        assert ga.shape == ma.shape
+        assert rel_l2(ga, torch.from_numpy(z["mel_after"])) < TOL_AR
+    else:
+        pytest.fail(f"golden case has stop margin {margin} <= 10 x logit error {err}; pick another seed")
+
+
+def test_persistent_equals_per_phase_launches(models):
+    """The cooperative persistent kernel and the one-launch-per-phase schedule run the same phase
+    code: results must be bit-identical."""
+    from oracle import synthetic
+    _, _, o, g = models
+    ph, pl, _, _ = synthetic.make_inputs(5, 20, 8, 43, ragged=True)
+    a1, l1, s1 = (t.cpu() for t in g.inference(ph.cuda(), pl.cuda(), max_len=24, seed=3))
+    g2 = make_b200_model(o, persistent=False)
+    a2, l2, s2 = (t.cpu() for t in g2.inference(ph.cuda(), pl.cuda(), max_len=24, seed=3))
+    assert l1.tolist() == l2.tolist()
+    assert torch.equal(a1, a2) and torch.equal(s1, s2)
+
+
+def test_sharded_equals_unsharded_bitwise(models):
+    """8(e): no collective on the inference path -- a shard with global utterance ids reproduces the
+    unsharded batch bit for bit."""
+    from oracle import synthetic
+    _, _, o, g = models
+    ph, pl, _, _ = synthetic.make_inputs(6, 24, 8, 44, ragged=False)
+    a, l, s = g.inference(ph, pl, max_len=20, seed=5)
+    for lo, hi in ((0, 3), (3, 6)):
+        a2, l2, s2 = g.inference(ph[lo:hi], pl[lo:hi], max_len=20, seed=5, utt_offset=lo)
+        T = a2.shape[1]
+        assert l2.tolist() == l[lo:hi].tolist()
+        assert torch.equal(a2, a[lo:hi, :T]) and torch.equal(s2, s[lo:hi, :T])
+
+
+def test_repeatable(models):
+    from oracle import synthetic
+    o, g, _, _ = models
+    ph, pl, _, _ = synthetic.make_inputs(2, 16, 8, 45, ragged=True)
+    a1, l1, s1 = g.inference(ph, pl, max_len=12, seed=9)
+    a2, l2, s2 = g.inference(ph, pl, max_len=12, seed=9)
+    assert torch.equal(a1, a2) and torch.equal(s1, s2)
+    a3, _, _ = g.inference(ph, pl, max_len=12, seed=10)
+    assert not torch.equal(a1, a3)                      # the dropout seed matters (P7)

@@ -1,0 +1,123 @@
+// Shared device helpers for the sm_100a Transformer-TTS kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+typedef __nv_bfloat16 bf16;
+
+#define TTS_HD __host__ __device__ __forceinline__
+#define TTS_D __device__ __forceinline__
+
+namespace tts {
+
+constexpr int kDModel = 512;     // the base model is the only model on this path
+constexpr int kHeads = 8;
+constexpr int kDHead = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ---------------------------------------------------------------- small utilities
+TTS_D uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+TTS_D float2 unpack_bf16x2(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+}
+TTS_D float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+TTS_D float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Loads of data that other CTAs of the SAME launch may have written (after a grid barrier):
+// L2-coherent, never served from a stale L1 line.
+TTS_D uint4 ld_cg_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+TTS_D float4 ld_cg_f4(const void* p) {
+    float4 r;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+TTS_D float2 ld_cg_f2(const void* p) {
+    float2 r;
+    asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+TTS_D float ld_cg_f(const void* p) {
+    float r;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+TTS_D int ld_cg_i(const void* p) {
+    int r;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+// L2 eviction policies (createpolicy): KV-cache rows are streamed once per step -> evict_first, so
+// they do not push the weights (re-read every step, 44.7 MB) out of the 126 MB L2 -> evict_last.
+TTS_D uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+TTS_D uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// Streaming KV-cache rows: L2-coherent (never allocated in L1), with an L2 cache-hint policy.
+TTS_D uint4 ld_stream_u4(const void* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+// Read-only for the whole launch (weights): non-coherent path.
+TTS_D uint4 ld_weight_u4(const void* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+
+// ---------------------------------------------------------------- warp-level bf16 MMA (m16n8k16)
+TTS_D void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+TTS_D void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+    uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+TTS_D void ldmatrix_x2(uint32_t& r0, uint32_t& r1, const void* smem_ptr) {
+    uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+TTS_D void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+    uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+TTS_D void cp_async_16(void* smem_ptr, const void* gptr, bool valid) {
+    uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    int sz = valid ? 16 : 0;                       // src-size 0 => 16 bytes of zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(addr), "l"(gptr), "r"(sz));
+}
+TTS_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+TTS_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+}  // namespace tts

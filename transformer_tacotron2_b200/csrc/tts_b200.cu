@@ -1,0 +1,738 @@
+// libtts_b200.so -- C ABI (include/tts_b200.h) over the sm_100a kernels.  Host-side orchestration:
+// weight packing, workspace carving, encoder / decode-loop / postnet / teacher-forced schedules.
+// No CPU fallback: every entry point launches CUDA kernels or fails.
+#include "../../include/tts_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "philox.cuh"
+#include "gemm_mma.cuh"
+#include "attention_mma.cuh"
+#include "misc_kernels.cuh"
+#include "decode.cuh"
+
+using namespace tts;
+
+// ------------------------------------------------------------------------------------------------
+struct TtsHandle {
+    TtsConfig cfg;
+    int device = 0, num_sms = 0;
+    std::string err;
+    std::map<std::string, std::vector<float>> staged;
+    bool finalized = false;
+    int decode_persistent = 1;
+    unsigned char* arena = nullptr; size_t arena_bytes = 0;
+    // ---- device weights (pointers into arena)
+    bf16* embed = nullptr;
+    bf16* enc_conv_w[3] = {}; float* enc_conv_b[3] = {};
+    bf16* enc_proj_w = nullptr; float* enc_proj_b = nullptr;
+    float enc_alpha = 1.f, dec_alpha = 1.f;
+    struct EncLayer { bf16 *wqkv, *wo, *w1, *w2; float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b; } enc[6];
+    bf16* ckv_w = nullptr; float* ckv_b = nullptr;                   // [6*1024][512]
+    struct DecLayer {
+        bf16 *wqkv, *wo, *wq2, *wo2, *w1, *w2;                       // row-major (teacher-forced GEMMs)
+        uint4 *pqkv, *po, *pq2, *po2, *p1, *p2;                      // fragment-packed (decode step)
+        float *bqkv, *bo, *bq2, *bo2, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b, *ln3g, *ln3b;
+    } dec[6];
+    bf16 *pre_fc1, *pre_fc2, *pre_proj, *head_w;
+    uint4 *ppre_fc1, *ppre_fc2, *ppre_proj, *phead;
+    float *pre_b1, *pre_b2, *pre_bp, *head_b;
+    bf16* post_w[5] = {}; float* post_b[5] = {};
+    float* pe = nullptr;
+    // ---- decode session
+    bool dec_active = false; int dec_B = 0, dec_S = 0, dec_T = 0, dec_t = 0; uint64_t dec_seed = 0; int dec_utt0 = 0;
+    DecodeParams dparams;
+    int* h_status = nullptr;                                          // pinned: t_done, n_finished
+};
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+            return (int)e_;                                                                          \
+        }                                                                                            \
+    } while (0)
+#define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline uint16_t f2bf(float f) {                                // round-to-nearest-even, as __float2bfloat16_rn
+    uint32_t u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Workspace layout
+struct Ws {
+    size_t total = 0;
+    size_t self_kv, cross_kv, mel_before, stop_logits, lens, finished, scalars, part_acc, part_ml, part_cnt, phases;
+    size_t d_xres, d_y, d_q, d_a, d_h, d_h1, d_h2;                    // decode-step activations
+    size_t x, x2, wide, a, y, mel16, mel32, ph, plens, mlens;         // sequence-parallel activations
+    static Ws make(int B, int S, int T) {
+        Ws w; size_t o = 0;
+        auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
+        const size_t Bp = (size_t)((B + 15) / 16) * 16, P = (size_t)B * kHeads;
+        const size_t M = (size_t)B * (size_t)(S > T ? S : T);
+        w.self_kv = take((size_t)6 * 2 * P * T * kDHead * 2);
+        w.cross_kv = take((size_t)6 * 2 * P * S * kDHead * 2);
+        w.mel_before = take((size_t)B * T * 80 * 4);
+        w.stop_logits = take((size_t)B * T * 4);
+        w.lens = take(B * 4); w.finished = take(B * 4); w.scalars = take(64);
+        w.part_acc = take(P * kMaxParts * kDHead * 4); w.part_ml = take(P * kMaxParts * 2 * 4); w.part_cnt = take(P * 4);
+        w.phases = take(64 * sizeof(PhaseDesc));
+        w.d_xres = take(Bp * 512 * 4); w.d_y = take(Bp * 512 * 4); w.d_q = take(Bp * 512 * 4);
+        w.d_a = take(Bp * 512 * 2); w.d_h = take(Bp * 2048 * 2); w.d_h1 = take(Bp * 256 * 2); w.d_h2 = take(Bp * 256 * 2);
+        w.x = take(M * 512 * 2); w.x2 = take(M * 512 * 2); w.wide = take(M * 2048 * 2); w.a = take(M * 512 * 2);
+        w.y = take(M * 512 * 4); w.mel16 = take(M * 96 * 2); w.mel32 = take(M * 80 * 4);
+        w.ph = take((size_t)B * S * 8); w.plens = take(B * 4); w.mlens = take(B * 4);
+        w.total = o;
+        return w;
+    }
+};
+template <typename T> static inline T* wsp(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ws) + off); }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* tts_version(void) { return "tts_b200 0.1 sm_100a"; }
+
+extern "C" const char* tts_last_error_string(TtsHandle* h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int tts_create(const TtsConfig* cfg, int device, TtsHandle** out) {
+    if (!cfg || !out || cfg->struct_size != sizeof(TtsConfig)) return TTS_E_ARG;
+    if (cfg->d_model != 512 || cfg->n_heads != 8 || cfg->d_ff != 2048 || cfg->n_mels != 80 || cfg->d_prenet != 256 ||
+        cfg->conv_kernel != 5 || cfg->n_enc_layers != 6 || cfg->n_dec_layers != 6 || cfg->enc_conv_layers != 3 ||
+        cfg->postnet_layers != 5 || cfg->postnet_channels != 512 || cfg->max_pos < 1 || cfg->n_vocab < 1)
+        return TTS_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return TTS_E_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return TTS_E_DEVICE;
+    TtsHandle* h = new TtsHandle();
+    h->cfg = *cfg; h->device = device; h->num_sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return TTS_E_DEVICE; }
+    if (cudaMallocHost(&h->h_status, 64) != cudaSuccess) { delete h; return TTS_E_DEVICE; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int tts_destroy(TtsHandle* h) {
+    if (!h) return TTS_E_ARG;
+    cudaSetDevice(h->device);
+    if (h->arena) cudaFree(h->arena);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    delete h;
+    return 0;
+}
+
+extern "C" int tts_set_option(TtsHandle* h, const char* key, int64_t value) {
+    if (!h || !key) return TTS_E_ARG;
+    if (!strcmp(key, "decode_persistent")) { h->decode_persistent = value ? 1 : 0; return 0; }
+    FAIL(TTS_E_ARG, std::string("unknown option ") + key);
+}
+
+extern "C" int tts_load_weight(TtsHandle* h, const char* name, const float* host_data, int64_t numel) {
+    if (!h || !name || !host_data || numel <= 0) return TTS_E_ARG;
+    h->staged[name].assign(host_data, host_data + numel);
+    h->finalized = false;
+    return 0;
+}
+
+// ---- packing helpers ---------------------------------------------------------------------------
+namespace {
+struct Arena {
+    std::vector<unsigned char> host;
+    size_t take(size_t bytes) { size_t o = align_up(host.size()); host.resize(o + bytes, 0); return o; }
+};
+
+// row-major bf16 [taps][Nw][Kp] from fp32 W laid out as w[(n * K + k) * taps + tap] (conv) or [n][k] (taps = 1),
+// scaled per output channel.
+size_t pack_rowmajor(Arena& ar, const float* w, int N, int K, int taps, int Nw, int Kp, const float* scale) {
+    size_t off = ar.take((size_t)taps * Nw * Kp * 2);
+    uint16_t* dst = reinterpret_cast<uint16_t*>(ar.host.data() + off);
+    for (int tap = 0; tap < taps; ++tap)
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < K; ++k) {
+                float v = w[((size_t)n * K + k) * taps + tap] * (scale ? scale[n] : 1.f);
+                dst[((size_t)tap * Nw + n) * Kp + k] = f2bf(v);
+            }
+    return off;
+}
+// mma.sync m16n8k16 B-fragment order: [Npad/8][Kp/32][32 lanes][4 x u32]
+size_t pack_fragments(Arena& ar, const float* w, int N, int K, int Npad, int Kp) {
+    const int kp_total = Kp / 32;
+    size_t off = ar.take((size_t)(Npad / 8) * kp_total * 32 * 16);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(ar.host.data() + off);
+    auto at = [&](int n, int k) -> uint32_t { return (n < N && k < K) ? f2bf(w[(size_t)n * K + k]) : 0; };
+    for (int j = 0; j < Npad / 8; ++j)
+        for (int kp = 0; kp < kp_total; ++kp)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t4 = lane & 3, n = j * 8 + g;
+                for (int qd = 0; qd < 4; ++qd) {
+                    const int s = kp * 2 + (qd >> 1), k = s * 16 + t4 * 2 + (qd & 1) * 8;
+                    dst[(((size_t)j * kp_total + kp) * 32 + lane) * 4 + qd] = at(n, k) | (at(n, k + 1) << 16);
+                }
+            }
+    return off;
+}
+size_t pack_f32(Arena& ar, const float* v, size_t n, size_t npad = 0) {
+    size_t off = ar.take((npad > n ? npad : n) * 4);
+    memcpy(ar.host.data() + off, v, n * 4);
+    return off;
+}
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+}  // namespace
+
+extern "C" int tts_finalize_weights(TtsHandle* h) {
+    if (!h) return TTS_E_ARG;
+    CK(cudaSetDevice(h->device));
+    const TtsConfig& c = h->cfg;
+    std::string missing;
+    auto get = [&](const std::string& k, size_t numel) -> const float* {
+        auto it = h->staged.find(k);
+        if (it == h->staged.end() || it->second.size() != numel) { missing = k; return nullptr; }
+        return it->second.data();
+    };
+#define GET(var, key, numel) const float* var = get(key, numel); if (!var) FAIL(TTS_E_WEIGHT, "missing or mis-sized weight: " + missing)
+    Arena ar;
+    struct Fix { void** dst; size_t off; };
+    std::vector<Fix> fixes;
+    auto bind = [&](auto** dst, size_t off) { fixes.push_back({reinterpret_cast<void**>(dst), off}); };
+    const int D = 512, F = 2048;
+
+    {   // embedding
+        GET(w, "enc_prenet.embed.weight", (size_t)c.n_vocab * D);
+        bind(&h->embed, pack_rowmajor(ar, w, c.n_vocab, D, 1, c.n_vocab, D, nullptr));
+    }
+    auto fold_conv = [&](const std::string& pre, int cin, int cout, int cin_pad, bf16** wd, float** bd) -> int {
+        GET(w, pre + ".conv.weight", (size_t)cout * cin * 5);
+        GET(b, pre + ".conv.bias", (size_t)cout);
+        GET(g, pre + ".bn.weight", (size_t)cout);
+        GET(be, pre + ".bn.bias", (size_t)cout);
+        GET(rm, pre + ".bn.running_mean", (size_t)cout);
+        GET(rv, pre + ".bn.running_var", (size_t)cout);
+        std::vector<float> sc(cout), bias(cout);
+        for (int o = 0; o < cout; ++o) {                              // P5: eval-mode BN folded into the conv
+            sc[o] = g[o] / std::sqrt(rv[o] + c.bn_eps);
+            bias[o] = (b[o] - rm[o]) * sc[o] + be[o];
+        }
+        bind(wd, pack_rowmajor(ar, w, cout, cin, 5, round_up(cout, 128), cin_pad, sc.data()));
+        bind(bd, pack_f32(ar, bias.data(), cout));
+        return 0;
+    };
+    for (int i = 0; i < 3; ++i) { int r = fold_conv("enc_prenet.convs." + std::to_string(i), D, D, D, &h->enc_conv_w[i], &h->enc_conv_b[i]); if (r) return r; }
+    for (int i = 0; i < 5; ++i) {
+        const int cin = i == 0 ? 80 : 512, cout = i == 4 ? 80 : 512;
+        int r = fold_conv("postnet.convs." + std::to_string(i), cin, cout, i == 0 ? 96 : 512, &h->post_w[i], &h->post_b[i]); if (r) return r;
+    }
+    auto linear_rm = [&](const std::string& pre, int N, int K, int Kp, bf16** wd, float** bd) -> int {
+        GET(w, pre + ".weight", (size_t)N * K); GET(b, pre + ".bias", (size_t)N);
+        bind(wd, pack_rowmajor(ar, w, N, K, 1, round_up(N, 128), Kp, nullptr));
+        bind(bd, pack_f32(ar, b, N, round_up(N, 128)));
+        return 0;
+    };
+    auto linear_frag = [&](const std::string& pre, int N, int K, int Kp, uint4** pd) -> int {
+        GET(w, pre + ".weight", (size_t)N * K);
+        bind(pd, pack_fragments(ar, w, N, K, round_up(N, 128), Kp));
+        return 0;
+    };
+    auto vec = [&](const std::string& key, int n, float** dst) -> int { GET(v, key, (size_t)n); bind(dst, pack_f32(ar, v, n)); return 0; };
+    auto cat3 = [&](const std::string& pre, std::vector<float>& w, std::vector<float>& b) -> int {
+        w.clear(); b.clear();
+        for (const char* nm : {"wq", "wk", "wv"}) {
+            GET(ww, pre + "." + nm + ".weight", (size_t)D * D); GET(bb, pre + "." + nm + ".bias", (size_t)D);
+            w.insert(w.end(), ww, ww + (size_t)D * D); b.insert(b.end(), bb, bb + D);
+        }
+        return 0;
+    };
+    int r;
+    if ((r = linear_rm("enc_prenet.proj", D, D, D, &h->enc_proj_w, &h->enc_proj_b))) return r;
+    { GET(a, "enc_alpha", 1); h->enc_alpha = a[0]; }
+    { GET(a, "dec_alpha", 1); h->dec_alpha = a[0]; }
+    std::vector<float> w3, b3;
+    for (int l = 0; l < 6; ++l) {
+        const std::string p = "encoder.layers." + std::to_string(l);
+        auto& L = h->enc[l];
+        if ((r = cat3(p + ".self_attn", w3, b3))) return r;
+        bind(&L.wqkv, pack_rowmajor(ar, w3.data(), 3 * D, D, 1, 3 * D, D, nullptr)); bind(&L.bqkv, pack_f32(ar, b3.data(), 3 * D));
+        if ((r = linear_rm(p + ".self_attn.wo", D, D, D, &L.wo, &L.bo))) return r;
+        if ((r = linear_rm(p + ".ffn.w1", F, D, D, &L.w1, &L.b1))) return r;
+        if ((r = linear_rm(p + ".ffn.w2", D, F, F, &L.w2, &L.b2))) return r;
+        if ((r = vec(p + ".norm1.weight", D, &L.ln1g)) || (r = vec(p + ".norm1.bias", D, &L.ln1b)) ||
+            (r = vec(p + ".norm2.weight", D, &L.ln2g)) || (r = vec(p + ".norm2.bias", D, &L.ln2b))) return r;
+    }
+    {   // hoisted cross-K/V projection of all 6 decoder layers as one [6*1024][512] weight
+        std::vector<float> w((size_t)6 * 1024 * D), b(6 * 1024);
+        for (int l = 0; l < 6; ++l) {
+            const std::string p = "decoder.layers." + std::to_string(l) + ".cross_attn";
+            GET(wk, p + ".wk.weight", (size_t)D * D); GET(wv, p + ".wv.weight", (size_t)D * D);
+            GET(bk, p + ".wk.bias", (size_t)D); GET(bv, p + ".wv.bias", (size_t)D);
+            memcpy(&w[(size_t)(l * 1024) * D], wk, (size_t)D * D * 4); memcpy(&w[(size_t)(l * 1024 + 512) * D], wv, (size_t)D * D * 4);
+            memcpy(&b[l * 1024], bk, D * 4); memcpy(&b[l * 1024 + 512], bv, D * 4);
+        }
+        bind(&h->ckv_w, pack_rowmajor(ar, w.data(), 6 * 1024, D, 1, 6 * 1024, D, nullptr));
+        bind(&h->ckv_b, pack_f32(ar, b.data(), 6 * 1024));
+    }
+    for (int l = 0; l < 6; ++l) {
+        const std::string p = "decoder.layers." + std::to_string(l);
+        auto& L = h->dec[l];
+        if ((r = cat3(p + ".self_attn", w3, b3))) return r;
+        bind(&L.wqkv, pack_rowmajor(ar, w3.data(), 3 * D, D, 1, 3 * D, D, nullptr)); bind(&L.bqkv, pack_f32(ar, b3.data(), 3 * D));
+        bind(&L.pqkv, pack_fragments(ar, w3.data(), 3 * D, D, 3 * D, D));
+        if ((r = linear_rm(p + ".self_attn.wo", D, D, D, &L.wo, &L.bo)) || (r = linear_frag(p + ".self_attn.wo", D, D, D, &L.po))) return r;
+        if ((r = linear_rm(p + ".cross_attn.wq", D, D, D, &L.wq2, &L.bq2)) || (r = linear_frag(p + ".cross_attn.wq", D, D, D, &L.pq2))) return r;
+        if ((r = linear_rm(p + ".cross_attn.wo", D, D, D, &L.wo2, &L.bo2)) || (r = linear_frag(p + ".cross_attn.wo", D, D, D, &L.po2))) return r;
+        if ((r = linear_rm(p + ".ffn.w1", F, D, D, &L.w1, &L.b1)) || (r = linear_frag(p + ".ffn.w1", F, D, D, &L.p1))) return r;
+        if ((r = linear_rm(p + ".ffn.w2", D, F, F, &L.w2, &L.b2)) || (r = linear_frag(p + ".ffn.w2", D, F, F, &L.p2))) return r;
+        if ((r = vec(p + ".norm1.weight", D, &L.ln1g)) || (r = vec(p + ".norm1.bias", D, &L.ln1b)) ||
+            (r = vec(p + ".norm2.weight", D, &L.ln2g)) || (r = vec(p + ".norm2.bias", D, &L.ln2b)) ||
+            (r = vec(p + ".norm3.weight", D, &L.ln3g)) || (r = vec(p + ".norm3.bias", D, &L.ln3b))) return r;
+    }
+    if ((r = linear_rm("dec_prenet.fc1", 256, 80, 96, &h->pre_fc1, &h->pre_b1)) || (r = linear_frag("dec_prenet.fc1", 256, 80, 96, &h->ppre_fc1))) return r;
+    if ((r = linear_rm("dec_prenet.fc2", 256, 256, 256, &h->pre_fc2, &h->pre_b2)) || (r = linear_frag("dec_prenet.fc2", 256, 256, 256, &h->ppre_fc2))) return r;
+    if ((r = linear_rm("dec_prenet.proj", 512, 256, 256, &h->pre_proj, &h->pre_bp)) || (r = linear_frag("dec_prenet.proj", 512, 256, 256, &h->ppre_proj))) return r;
+    {   // [mel | stop] heads fused into one 81-row matrix (C7)
+        GET(wm, "mel_linear.weight", (size_t)80 * D); GET(bm, "mel_linear.bias", 80);
+        GET(wsx, "stop_linear.weight", (size_t)D); GET(bs, "stop_linear.bias", 1);
+        std::vector<float> w((size_t)81 * D), b(81);
+        memcpy(w.data(), wm, (size_t)80 * D * 4); memcpy(&w[(size_t)80 * D], wsx, D * 4);
+        memcpy(b.data(), bm, 80 * 4); b[80] = bs[0];
+        bind(&h->head_w, pack_rowmajor(ar, w.data(), 81, D, 1, 128, D, nullptr));
+        bind(&h->phead, pack_fragments(ar, w.data(), 81, D, 128, D));
+        bind(&h->head_b, pack_f32(ar, b.data(), 81, 128));
+    }
+    {   // P4 sinusoid table, fp32 rounded from float64 (same definition as oracle.sinusoid_table)
+        std::vector<float> pe((size_t)c.max_pos * D);
+        for (int pos = 0; pos < c.max_pos; ++pos)
+            for (int i = 0; i < D; i += 2) {
+                const double ang = (double)pos / std::pow(10000.0, (double)i / D);
+                pe[(size_t)pos * D + i] = (float)std::sin(ang); pe[(size_t)pos * D + i + 1] = (float)std::cos(ang);
+            }
+        bind(&h->pe, pack_f32(ar, pe.data(), pe.size()));
+    }
+#undef GET
+    if (h->arena) { cudaFree(h->arena); h->arena = nullptr; }
+    h->arena_bytes = align_up(ar.host.size());
+    CK(cudaMalloc(&h->arena, h->arena_bytes));
+    CK(cudaMemcpy(h->arena, ar.host.data(), ar.host.size(), cudaMemcpyHostToDevice));
+    for (auto& f : fixes) *f.dst = h->arena + f.off;
+    CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes));
+    CK(cudaDeviceSynchronize());
+    h->finalized = true;
+    h->staged.clear();
+    return 0;
+}
+
+extern "C" size_t tts_workspace_bytes(TtsHandle* h, int B, int S, int T) {
+    if (!h || B <= 0 || S <= 0 || T <= 0) return 0;
+    return Ws::make(B, S, T).total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sequence-parallel building blocks
+namespace {
+GemmParams gp(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K) {
+    GemmParams p; memset(&p, 0, sizeof(p));
+    p.A = A; p.lda = lda; p.W = W; p.ldw = ldw; p.M = M; p.N = N; p.K = K; p.taps = 1; p.Nw = round_up(N, 128);
+    p.T = M; p.drop_site = -1; p.B = 1;
+    return p;
+}
+AttnParams ap_packed(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
+                     int B, int Lq, int Lk, const int* klens, int causal) {
+    AttnParams a; memset(&a, 0, sizeof(a));
+    a.Q = Q; a.K = K; a.V = V; a.O = O;
+    a.q_bs = (long)Lq * ldq; a.q_hs = 64; a.q_rs = ldq;
+    a.k_bs = (long)Lk * ldk; a.k_hs = 64; a.k_rs = ldk;
+    a.v_bs = (long)Lk * ldv; a.v_hs = 64; a.v_rs = ldv;
+    a.o_bs = (long)Lq * ldo; a.o_hs = 64; a.o_rs = ldo;
+    a.B = B; a.H = kHeads; a.Lq = Lq; a.Lk = Lk; a.klens = klens; a.causal = causal;
+    a.scale_log2 = 0.125f * kLog2e;
+    return a;
+}
+cudaError_t layernorm(const float* x, const float* g, const float* b, bf16* o16, float* o32, int M, float eps, cudaStream_t st) {
+    layernorm512_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, g, b, o16, o32, M, eps);
+    return cudaGetLastError();
+}
+}  // namespace
+
+#define CKL(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return (int)e_; } } while (0)
+
+// Encoder (C1-C4) + hoisted cross-K/V projection.  Result: memory in ws.x (bf16 [B*S][512]).
+static int run_encoder(TtsHandle* h, void* ws, const Ws& L, const int64_t* ph, const int* plens, int B, int S, cudaStream_t st) {
+    const int M = B * S;
+    bf16 *x = wsp<bf16>(ws, L.x), *x2 = wsp<bf16>(ws, L.x2), *wide = wsp<bf16>(ws, L.wide), *a = wsp<bf16>(ws, L.a);
+    float* y = wsp<float>(ws, L.y);
+    embed_kernel<<<(M + 3) / 4, 256, 0, st>>>(ph, plens, h->embed, x, B, S, h->cfg.n_vocab);
+    CKL(cudaGetLastError());
+    for (int i = 0; i < 3; ++i) {                                      // conv k5 + folded BN + ReLU + length mask
+        GemmParams p = gp(x, 512, h->enc_conv_w[i], 512, M, 512, 512);
+        p.taps = 5; p.T = S; p.bias = h->enc_conv_b[i]; p.act = ACT_RELU; p.lens = plens; p.out_bf16 = x2; p.ldo = 512;
+        CKL(launch_gemm(p, st));
+        std::swap(x, x2);
+    }
+    {   // linear + alpha * PE
+        GemmParams p = gp(x, 512, h->enc_proj_w, 512, M, 512, 512);
+        p.T = S; p.bias = h->enc_proj_b; p.pe = h->pe; p.alpha = h->enc_alpha; p.out_bf16 = x2; p.ldo = 512;
+        CKL(launch_gemm(p, st));
+        std::swap(x, x2);
+    }
+    for (int l = 0; l < 6; ++l) {
+        auto& W = h->enc[l];
+        GemmParams p = gp(x, 512, W.wqkv, 512, M, 1536, 512); p.bias = W.bqkv; p.out_bf16 = wide; p.ldo = 1536;
+        CKL(launch_gemm(p, st));
+        AttnParams at = ap_packed(wide, 1536, wide + 512, 1536, wide + 1024, 1536, a, 512, B, S, S, plens, 0);
+        CKL(launch_flash_attn(at, st));
+        p = gp(a, 512, W.wo, 512, M, 512, 512); p.bias = W.bo; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
+        CKL(launch_gemm(p, st));
+        CKL(layernorm(y, W.ln1g, W.ln1b, x, nullptr, M, h->cfg.ln_eps, st));
+        p = gp(x, 512, W.w1, 512, M, 2048, 512); p.bias = W.b1; p.act = ACT_RELU; p.out_bf16 = wide; p.ldo = 2048;
+        CKL(launch_gemm(p, st));
+        p = gp(wide, 2048, W.w2, 2048, M, 512, 2048); p.bias = W.b2; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
+        CKL(launch_gemm(p, st));
+        CKL(layernorm(y, W.ln2g, W.ln2b, x, nullptr, M, h->cfg.ln_eps, st));
+    }
+    if (x != wsp<bf16>(ws, L.x)) {                                     // keep memory in ws.x
+        CKL(cudaMemcpyAsync(wsp<bf16>(ws, L.x), x, (size_t)M * 512 * 2, cudaMemcpyDeviceToDevice, st));
+    }
+    {   // cross K/V of all decoder layers -> cache [6][2][B][H][S][64]
+        GemmParams p = gp(wsp<bf16>(ws, L.x), 512, h->ckv_w, 512, M, 6 * 1024, 512);
+        p.T = S; p.B = B; p.bias = h->ckv_b; p.scatter = SC_CROSS_KV; p.out_bf16 = wsp<bf16>(ws, L.cross_kv);
+        CKL(launch_gemm(p, st));
+    }
+    return 0;
+}
+
+// Postnet (C8) over compact rows: in16 bf16 [B*T][96] masked, resid32 fp32 [B*T][80] masked -> mel_after [B*T][80].
+static int run_postnet(TtsHandle* h, void* ws, const Ws& L, const int* mlens, int B, int T, float* mel_after, cudaStream_t st) {
+    const int M = B * T;
+    bf16 *x = wsp<bf16>(ws, L.x2), *x2 = wsp<bf16>(ws, L.a);
+    const bf16* in = wsp<bf16>(ws, L.mel16);
+    for (int i = 0; i < 5; ++i) {
+        const int K = i == 0 ? 96 : 512, N = i == 4 ? 80 : 512;
+        GemmParams p = gp(in, K, h->post_w[i], K, M, N, K);
+        p.taps = 5; p.T = T; p.bias = h->post_b[i]; p.lens = mlens;
+        if (i < 4) { p.act = ACT_TANH; p.out_bf16 = x; p.ldo = 512; }
+        else { p.resid_f32 = wsp<float>(ws, L.mel32); p.ldr = 80; p.out_f32 = mel_after; p.ldo = 80; }
+        CKL(launch_gemm(p, st));
+        in = x; std::swap(x, x2);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int tts_encode(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* phoneme_lens, int B, int S, int T,
+                          float* memory_out, void* stream) {
+    if (!h || !ws || !phonemes || !phoneme_lens || B <= 0 || S <= 0 || T <= 0) return TTS_E_ARG;
+    if (!h->finalized) FAIL(TTS_E_STATE, "weights not finalised");
+    if (S > h->cfg.max_pos) FAIL(TTS_E_ARG, "S exceeds max_pos");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Ws L = Ws::make(B, S, T);
+    // the decode phases read the key-padding lengths from the workspace copy
+    CK(cudaMemcpyAsync(wsp<int>(ws, L.plens), phoneme_lens, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    int r = run_encoder(h, ws, L, phonemes, wsp<int>(ws, L.plens), B, S, st);
+    if (r) return r;
+    if (memory_out) {
+        size_t n = (size_t)B * S * 512;
+        bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wsp<bf16>(ws, L.x), memory_out, n);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+static int choose_nt(int N, int K, int mtiles, int ncta) {
+    int best = 16;
+    for (int nt = 16; nt >= 1; nt >>= 1) {
+        const int ks = 16 / nt;
+        if ((K / 32) % ks != 0) continue;
+        const int items = ((N + nt * 8 - 1) / (nt * 8)) * mtiles;
+        if (items <= ncta) best = nt; else break;
+    }
+    return best;
+}
+
+extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_len, uint64_t seed, int utt_offset, void* stream) {
+    if (!h || !ws || B <= 0 || S <= 0 || max_len <= 0) return TTS_E_ARG;
+    if (!h->finalized) FAIL(TTS_E_STATE, "weights not finalised");
+    if (max_len > h->cfg.max_pos) FAIL(TTS_E_ARG, "max_len exceeds max_pos");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Ws L = Ws::make(B, S, max_len);
+    h->dec_active = true; h->dec_B = B; h->dec_S = S; h->dec_T = max_len; h->dec_t = 0; h->dec_seed = seed; h->dec_utt0 = utt_offset;
+    const int P = B * kHeads;
+    init_decode_state_kernel<<<(std::max(P, 4) + 255) / 256, 256, 0, st>>>(wsp<int>(ws, L.lens), wsp<int>(ws, L.finished),
+                                                                          wsp<int>(ws, L.scalars), wsp<unsigned>(ws, L.part_cnt), B, max_len, P);
+    CK(cudaGetLastError());
+
+    float *xres = wsp<float>(ws, L.d_xres), *y = wsp<float>(ws, L.d_y), *q = wsp<float>(ws, L.d_q);
+    bf16 *abuf = wsp<bf16>(ws, L.d_a), *hbuf = wsp<bf16>(ws, L.d_h), *h1 = wsp<bf16>(ws, L.d_h1), *h2 = wsp<bf16>(ws, L.d_h2);
+    bf16 *skv = wsp<bf16>(ws, L.self_kv), *ckv = wsp<bf16>(ws, L.cross_kv);
+    const int* plens = wsp<int>(ws, L.plens);
+    const int mtiles = (B + 15) / 16, ncta = h->num_sms;
+    std::vector<PhaseDesc> ph; ph.reserve(64);
+    auto gemm = [&](int N, int K, int Kreal, int a_kind, const void* a, int lda, const uint4* w, const float* bias, int epi) {
+        PhaseDesc d; memset(&d, 0, sizeof(d));
+        d.type = PH_GEMM; d.N = N; d.K = K; d.Kreal = Kreal; d.nt = choose_nt(N, K, mtiles, ncta);
+        d.a_kind = a_kind; d.a = a; d.lda = lda; d.w = w; d.bias = bias; d.epi = epi; d.ldo = N;
+        ph.push_back(d); return &ph.back();
+    };
+    auto attn = [&](const bf16* kc, const bf16* vc, int Lmax, int Lfixed, const int* lens) {
+        PhaseDesc d; memset(&d, 0, sizeof(d));
+        d.type = PH_ATTN; d.q = q; d.kc = kc; d.vc = vc; d.Lmax = Lmax; d.L_fixed = Lfixed; d.lens = lens; d.attn_out = abuf;
+        ph.push_back(d);
+    };
+    PhaseDesc* d;
+    d = gemm(256, 96, 80, A_FRAME, nullptr, 0, h->ppre_fc1, h->pre_b1, EPI_DROP_BF16); d->out_bf16 = h1; d->site = SITE_DEC_PRENET_FC1;
+    d = gemm(256, 256, 256, A_BF16, h1, 256, h->ppre_fc2, h->pre_b2, EPI_DROP_BF16); d->out_bf16 = h2; d->site = SITE_DEC_PRENET_FC2;
+    d = gemm(512, 256, 256, A_BF16, h2, 256, h->ppre_proj, h->pre_bp, EPI_PE_F32); d->out_f32 = xres;
+    const size_t kv_layer = (size_t)P * max_len * kDHead, ckv_layer = (size_t)P * S * kDHead;
+    for (int l = 0; l < 6; ++l) {
+        auto& W = h->dec[l];
+        if (l == 0) d = gemm(1536, 512, 512, A_F32, xres, 512, W.pqkv, W.bqkv, EPI_QKV);
+        else { d = gemm(1536, 512, 512, A_F32_LN, y, 512, W.pqkv, W.bqkv, EPI_QKV); d->ln_g = h->dec[l - 1].ln3g; d->ln_b = h->dec[l - 1].ln3b; d->xres_out = xres; }
+        d->out_f32 = q; d->layer = l;
+        attn(skv + (size_t)(l * 2) * kv_layer, skv + (size_t)(l * 2 + 1) * kv_layer, max_len, 0, nullptr);
+        d = gemm(512, 512, 512, A_BF16, abuf, 512, W.po, W.bo, EPI_RESID_F32); d->resid = xres; d->out_f32 = y;
+        d = gemm(512, 512, 512, A_F32_LN, y, 512, W.pq2, W.bq2, EPI_F32); d->ln_g = W.ln1g; d->ln_b = W.ln1b; d->xres_out = xres; d->out_f32 = q;
+        attn(ckv + (size_t)(l * 2) * ckv_layer, ckv + (size_t)(l * 2 + 1) * ckv_layer, S, S, plens);
+        d = gemm(512, 512, 512, A_BF16, abuf, 512, W.po2, W.bo2, EPI_RESID_F32); d->resid = xres; d->out_f32 = y;
+        d = gemm(2048, 512, 512, A_F32_LN, y, 512, W.p1, W.b1, EPI_RELU_BF16); d->ln_g = W.ln2g; d->ln_b = W.ln2b; d->xres_out = xres; d->out_bf16 = hbuf;
+        d = gemm(512, 2048, 2048, A_BF16, hbuf, 2048, W.p2, W.b2, EPI_RESID_F32); d->resid = xres; d->out_f32 = y;
+    }
+    d = gemm(81, 512, 512, A_F32_LN, y, 512, h->phead, h->head_b, EPI_HEAD); d->ln_g = h->dec[5].ln3g; d->ln_b = h->dec[5].ln3b;
+    if (ph.size() > 64) FAIL(TTS_E_STATE, "phase table overflow");
+    CK(cudaMemcpyAsync(wsp<PhaseDesc>(ws, L.phases), ph.data(), ph.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                                      // ph is a stack vector
+
+    DecodeParams& p = h->dparams; memset(&p, 0, sizeof(p));
+    p.phases = wsp<PhaseDesc>(ws, L.phases); p.n_phases = (int)ph.size();
+    p.B = B; p.Tmax = max_len; p.S = S; p.seed = seed; p.utt_offset = utt_offset;
+    p.dec_alpha = h->dec_alpha; p.pe = h->pe; p.self_kv = skv;
+    p.mel_before = wsp<float>(ws, L.mel_before); p.stop_logits = wsp<float>(ws, L.stop_logits);
+    p.lens = wsp<int>(ws, L.lens); p.finished = wsp<int>(ws, L.finished);
+    int* sc = wsp<int>(ws, L.scalars);
+    p.n_finished = sc; p.t_done = sc + 1; p.barrier = reinterpret_cast<unsigned*>(sc + 2);
+    p.part_acc = wsp<float>(ws, L.part_acc); p.part_ml = wsp<float>(ws, L.part_ml); p.part_cnt = wsp<unsigned>(ws, L.part_cnt);
+    return 0;
+}
+
+extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* stream) {
+    if (!h || !ws || n_steps < 0) return TTS_E_ARG;
+    if (!h->dec_active) FAIL(TTS_E_STATE, "tts_decode_begin not called");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    n_steps = std::min(n_steps, h->dec_T - h->dec_t);
+    if (n_steps <= 0) return 0;
+    DecodeParams p = h->dparams;
+    const int grid = h->num_sms;
+    if (h->decode_persistent) {
+        CK(cudaMemsetAsync(p.barrier, 0, 4, st));
+        int t0 = h->dec_t, ns = n_steps, pb = 0, pe = p.n_phases, pers = 1;
+        void* args[] = {&p, &t0, &ns, &pb, &pe, &pers};
+        CK(cudaLaunchCooperativeKernel((void*)decode_kernel, dim3(grid), dim3(kDecThreads), args, kDecSmemBytes, st));
+    } else {
+        for (int s = 0; s < n_steps; ++s)
+            for (int phs = 0; phs < p.n_phases; ++phs) {
+                decode_kernel<<<grid, kDecThreads, kDecSmemBytes, st>>>(p, h->dec_t + s, 1, phs, phs + 1, 0);
+                CK(cudaGetLastError());
+            }
+        int td = h->dec_t + n_steps;
+        CK(cudaMemcpyAsync(p.t_done, &td, 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    h->dec_t += n_steps;                                                // upper bound; tts_decode_status refines it
+    return 0;
+}
+
+extern "C" int tts_decode_status(TtsHandle* h, void* ws, int* t_done, int* n_finished, void* stream) {
+    if (!h || !ws) return TTS_E_ARG;
+    if (!h->dec_active) FAIL(TTS_E_STATE, "tts_decode_begin not called");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(h->h_status, h->dparams.n_finished, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_finished) *n_finished = h->h_status[0];
+    if (t_done) *t_done = h->h_status[1];
+    if (h->h_status[0] >= h->dec_B) h->dec_t = h->h_status[1];        // early exit on the device
+    return 0;
+}
+
+extern "C" int tts_decode_end(TtsHandle* h, void* ws, int T_out, float* mel_after, int32_t* mel_lens, float* stop_logits,
+                              float* mel_before, void* stream) {
+    if (!h || !ws || !mel_after || T_out <= 0) return TTS_E_ARG;
+    if (!h->dec_active) FAIL(TTS_E_STATE, "tts_decode_begin not called");
+    if (T_out > h->dec_T) FAIL(TTS_E_ARG, "T_out exceeds max_len");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = h->dec_B;
+    const Ws L = Ws::make(B, h->dec_S, h->dec_T);
+    const int* lens = wsp<int>(ws, L.lens);
+    const int n = B * T_out * 24;
+    mel_to_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(wsp<float>(ws, L.mel_before), h->dec_T, lens, 0,
+                                                        wsp<bf16>(ws, L.mel16), wsp<float>(ws, L.mel32), B, T_out);
+    CK(cudaGetLastError());
+    if (stop_logits || mel_lens) {
+        float* so = stop_logits ? stop_logits : wsp<float>(ws, L.y);
+        finalize_stop_kernel<<<(std::max(B * T_out, B) + 255) / 256, 256, 0, st>>>(wsp<float>(ws, L.stop_logits), h->dec_T, lens, so, mel_lens, B, T_out);
+        CK(cudaGetLastError());
+    }
+    if (mel_before) CK(cudaMemcpyAsync(mel_before, wsp<float>(ws, L.mel32), (size_t)B * T_out * 80 * 4, cudaMemcpyDeviceToDevice, st));
+    return run_postnet(h, ws, L, lens, B, T_out, mel_after, st);
+}
+
+extern "C" int tts_infer_host(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* phoneme_lens, int B, int S,
+                              int max_len, uint64_t seed, int utt_offset, float* mel_after, int32_t* mel_lens,
+                              float* stop_logits, int* T_out, void* stream) {
+    if (!h || !ws || !phonemes || !phoneme_lens || !mel_after || !mel_lens || !stop_logits || !T_out) return TTS_E_ARG;
+    if (!h->finalized) FAIL(TTS_E_STATE, "weights not finalised");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Ws L = Ws::make(B, S, max_len);
+    CK(cudaMemcpyAsync(wsp<int64_t>(ws, L.ph), phonemes, (size_t)B * S * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(wsp<int>(ws, L.plens), phoneme_lens, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    int r = tts_decode_begin(h, ws, B, S, max_len, seed, utt_offset, stream);   // fixes the layout (T = max_len) first
+    if (r) return r;
+    if ((r = run_encoder(h, ws, L, wsp<int64_t>(ws, L.ph), wsp<int>(ws, L.plens), B, S, st))) return r;
+    int td = 0, nf = 0;
+    if (h->decode_persistent) {
+        if ((r = tts_decode_steps(h, ws, max_len, stream))) return r;       // exits on the device when all fired
+        if ((r = tts_decode_status(h, ws, &td, &nf, stream))) return r;
+    } else {
+        while (h->dec_t < max_len) {
+            if ((r = tts_decode_steps(h, ws, 16, stream))) return r;
+            if ((r = tts_decode_status(h, ws, &td, &nf, stream))) return r;
+            if (nf >= B) break;
+        }
+        if (nf >= B) {                                                      // first step at which all had fired
+            std::vector<int> lens(B);
+            CK(cudaMemcpy(lens.data(), wsp<int>(ws, L.lens), B * 4, cudaMemcpyDeviceToHost));
+            td = 0; for (int v : lens) td = std::max(td, v);
+        }
+    }
+    // outputs staged in the (now free) sequence buffers, then copied to the host
+    float* d_after = wsp<float>(ws, L.y);
+    float* d_stop = reinterpret_cast<float*>(wsp<bf16>(ws, L.wide));
+    int* d_lens = wsp<int>(ws, L.mlens);
+    if ((r = tts_decode_end(h, ws, td, d_after, d_lens, d_stop, nullptr, stream))) return r;
+    CK(cudaMemcpyAsync(mel_after, d_after, (size_t)B * td * 80 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(stop_logits, d_stop, (size_t)B * td * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(mel_lens, d_lens, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *T_out = td;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* phoneme_lens, const float* mels,
+                           const int32_t* mel_lens, int B, int S, int T, uint64_t seed, int utt_offset, float* mel_before,
+                           float* mel_after, float* stop_logits, void* stream) {
+    if (!h || !ws || !phonemes || !phoneme_lens || !mels || !mel_lens || !mel_before || !mel_after || !stop_logits) return TTS_E_ARG;
+    if (B <= 0 || S <= 0 || T <= 0) return TTS_E_ARG;
+    if (!h->finalized) FAIL(TTS_E_STATE, "weights not finalised");
+    if (S > h->cfg.max_pos || T > h->cfg.max_pos) FAIL(TTS_E_ARG, "sequence exceeds max_pos");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Ws L = Ws::make(B, S, T);
+    int r = run_encoder(h, ws, L, phonemes, phoneme_lens, B, S, st);
+    if (r) return r;
+    const int M = B * T;
+    // decoder activations must not alias the memory kept in ws.x during cross-attention: cross K/V is
+    // already in the cache, so ws.x is free again.
+    bf16 *x = wsp<bf16>(ws, L.x), *x2 = wsp<bf16>(ws, L.x2), *wide = wsp<bf16>(ws, L.wide), *a = wsp<bf16>(ws, L.a);
+    float* y = wsp<float>(ws, L.y);
+    bf16* mel16 = wsp<bf16>(ws, L.mel16);
+    {   // P8: shift right, zero go-frame
+        const int n = M * 24;
+        mel_to_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(mels, T, mel_lens, 1, mel16, nullptr, B, T);
+        CK(cudaGetLastError());
+    }
+    {   // decoder prenet: dropout ALWAYS on (P7), masks keyed by (site, t, global utterance id)
+        GemmParams p = gp(mel16, 96, h->pre_fc1, 96, M, 256, 96);
+        p.T = T; p.bias = h->pre_b1; p.act = ACT_RELU; p.drop_site = SITE_DEC_PRENET_FC1; p.seed = seed; p.utt_offset = utt_offset; p.out_bf16 = x; p.ldo = 256;
+        CK(launch_gemm(p, st));
+        p = gp(x, 256, h->pre_fc2, 256, M, 256, 256);
+        p.T = T; p.bias = h->pre_b2; p.act = ACT_RELU; p.drop_site = SITE_DEC_PRENET_FC2; p.seed = seed; p.utt_offset = utt_offset; p.out_bf16 = x2; p.ldo = 256;
+        CK(launch_gemm(p, st));
+        p = gp(x2, 256, h->pre_proj, 256, M, 512, 256);
+        p.T = T; p.bias = h->pre_bp; p.pe = h->pe; p.alpha = h->dec_alpha; p.out_bf16 = x; p.ldo = 512;
+        CK(launch_gemm(p, st));
+    }
+    const bf16* ckv = wsp<bf16>(ws, L.cross_kv);
+    const size_t ckv_layer = (size_t)B * kHeads * S * kDHead;
+    for (int l = 0; l < 6; ++l) {
+        auto& W = h->dec[l];
+        GemmParams p = gp(x, 512, W.wqkv, 512, M, 1536, 512); p.bias = W.bqkv; p.out_bf16 = wide; p.ldo = 1536;
+        CK(launch_gemm(p, st));
+        AttnParams at = ap_packed(wide, 1536, wide + 512, 1536, wide + 1024, 1536, a, 512, B, T, T, mel_lens, 1);
+        CK(launch_flash_attn(at, st));
+        p = gp(a, 512, W.wo, 512, M, 512, 512); p.bias = W.bo; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
+        CK(launch_gemm(p, st));
+        CK(layernorm(y, W.ln1g, W.ln1b, x, nullptr, M, h->cfg.ln_eps, st));
+        p = gp(x, 512, W.wq2, 512, M, 512, 512); p.bias = W.bq2; p.out_bf16 = x2; p.ldo = 512;
+        CK(launch_gemm(p, st));
+        at = ap_packed(x2, 512, nullptr, 64, nullptr, 64, a, 512, B, T, S, phoneme_lens, 0);
+        at.K = ckv + (size_t)(l * 2) * ckv_layer; at.V = ckv + (size_t)(l * 2 + 1) * ckv_layer;     // [B][H][S][64]
+        at.k_bs = at.v_bs = (long)kHeads * S * kDHead; at.k_hs = at.v_hs = (long)S * kDHead; at.k_rs = at.v_rs = kDHead;
+        CK(launch_flash_attn(at, st));
+        p = gp(a, 512, W.wo2, 512, M, 512, 512); p.bias = W.bo2; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
+        CK(launch_gemm(p, st));
+        CK(layernorm(y, W.ln2g, W.ln2b, x, nullptr, M, h->cfg.ln_eps, st));
+        p = gp(x, 512, W.w1, 512, M, 2048, 512); p.bias = W.b1; p.act = ACT_RELU; p.out_bf16 = wide; p.ldo = 2048;
+        CK(launch_gemm(p, st));
+        p = gp(wide, 2048, W.w2, 2048, M, 512, 2048); p.bias = W.b2; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
+        CK(launch_gemm(p, st));
+        CK(layernorm(y, W.ln3g, W.ln3b, x, nullptr, M, h->cfg.ln_eps, st));
+    }
+    {   // [mel | stop] heads, zeroed past mel_lens
+        GemmParams p = gp(x, 512, h->head_w, 512, M, 81, 512);
+        p.T = T; p.bias = h->head_b; p.lens = mel_lens; p.scatter = SC_HEAD; p.out_f32 = mel_before; p.out2_f32 = stop_logits;
+        CK(launch_gemm(p, st));
+    }
+    {
+        const int n = M * 24;
+        mel_to_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(mel_before, T, mel_lens, 0, mel16, wsp<float>(ws, L.mel32), B, T);
+        CK(cudaGetLastError());
+    }
+    return run_postnet(h, ws, L, mel_lens, B, T, mel_after, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-kernel test entry points
+extern "C" int tts_k_gemm(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int act, void* stream) {
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || (K % 32) || (N % 128)) return TTS_E_ARG;
+    GemmParams p = gp((const bf16*)A, K, (const bf16*)W, K, M, N, K);
+    p.bias = bias; p.act = act; p.out_f32 = C; p.ldo = N;
+    return (int)launch_gemm(p, (cudaStream_t)stream);
+}
+extern "C" int tts_k_conv5(const void* X, const void* W, const float* bias, const int32_t* lens, float* Y, int B, int T, int Cin,
+                           int Cout, int act, void* stream) {
+    if (!X || !W || !Y || B <= 0 || T <= 0 || (Cin % 32) || (Cout % 128)) return TTS_E_ARG;
+    GemmParams p = gp((const bf16*)X, Cin, (const bf16*)W, Cin, B * T, Cout, Cin);
+    p.taps = 5; p.T = T; p.bias = bias; p.act = act; p.lens = lens; p.out_f32 = Y; p.ldo = Cout;
+    return (int)launch_gemm(p, (cudaStream_t)stream);
+}
+extern "C" int tts_k_attention(const void* Q, const void* K, const void* V, void* O, const int32_t* klens, int B, int H, int Lq,
+                               int Lk, int causal, void* stream) {
+    if (!Q || !K || !V || !O || B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return TTS_E_ARG;
+    const int ld = H * 64;
+    AttnParams a = ap_packed((const bf16*)Q, ld, (const bf16*)K, ld, (const bf16*)V, ld, (bf16*)O, ld, B, Lq, Lk, klens, causal);
+    a.H = H;
+    return (int)launch_flash_attn(a, (cudaStream_t)stream);
+}
+extern "C" int tts_k_layernorm(const float* X, const float* gamma, const float* beta, void* Y, int M, float eps, void* stream) {
+    if (!X || !gamma || !beta || !Y || M <= 0) return TTS_E_ARG;
+    return (int)layernorm(X, gamma, beta, (bf16*)Y, nullptr, M, eps, (cudaStream_t)stream);
+}
+extern "C" int tts_k_philox_bits(uint64_t seed, int site, int T, int B, int C, int utt_offset, uint8_t* out, void* stream) {
+    if (!out || T <= 0 || B <= 0 || C <= 0) return TTS_E_ARG;
+    const int n = T * B * C;
+    philox_bits_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seed, site, T, B, C, utt_offset, out);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,304 @@
+"""B200 backend of the Transformer-TTS module API.
+
+Same class name, method signatures and state_dict keys as the interface BASELINE.json `north_star`
+defines (restated executable in oracle/transformer_tts.py:TransformerTTS; the reference repository
+itself ships no code, /root/reference/README.md:1-3).  All arithmetic happens in libtts_b200.so
+(hand-written sm_100a kernels behind the C ABI of include/tts_b200.h); PyTorch is used for device
+memory, streams and the nn.Module parameter container only.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, asdict
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+@dataclass(frozen=True)
+class TTSConfig:
+    n_vocab: int = 128
+    d_model: int = 512
+    n_heads: int = 8
+    n_enc_layers: int = 6
+    n_dec_layers: int = 6
+    d_ff: int = 2048
+    n_mels: int = 80
+    d_prenet: int = 256
+    enc_conv_layers: int = 3
+    conv_kernel: int = 5
+    postnet_channels: int = 512
+    postnet_layers: int = 5
+    max_pos: int = 2048
+    ln_eps: float = 1e-5
+    bn_eps: float = 1e-5
+
+    def to_dict(self):
+        return asdict(self)
+
+
+# ---- parameter containers: the state_dict layout of the module API -----------------------------
+class _MHA(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.wq, self.wk, self.wv, self.wo = (nn.Linear(d, d) for _ in range(4))
+
+
+class _FFN(nn.Module):
+    def __init__(self, d, f):
+        super().__init__()
+        self.w1, self.w2 = nn.Linear(d, f), nn.Linear(f, d)
+
+
+class _EncLayer(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.self_attn = _MHA(c.d_model)
+        self.norm1 = nn.LayerNorm(c.d_model, eps=c.ln_eps)
+        self.ffn = _FFN(c.d_model, c.d_ff)
+        self.norm2 = nn.LayerNorm(c.d_model, eps=c.ln_eps)
+
+
+class _DecLayer(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.self_attn = _MHA(c.d_model)
+        self.norm1 = nn.LayerNorm(c.d_model, eps=c.ln_eps)
+        self.cross_attn = _MHA(c.d_model)
+        self.norm2 = nn.LayerNorm(c.d_model, eps=c.ln_eps)
+        self.ffn = _FFN(c.d_model, c.d_ff)
+        self.norm3 = nn.LayerNorm(c.d_model, eps=c.ln_eps)
+
+
+class _ConvBN(nn.Module):
+    def __init__(self, cin, cout, k, eps):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, k, padding=(k - 1) // 2)
+        self.bn = nn.BatchNorm1d(cout, eps=eps)
+
+
+class _EncPrenet(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.embed = nn.Embedding(c.n_vocab, c.d_model, padding_idx=0)
+        self.convs = nn.ModuleList(_ConvBN(c.d_model, c.d_model, c.conv_kernel, c.bn_eps) for _ in range(c.enc_conv_layers))
+        self.proj = nn.Linear(c.d_model, c.d_model)
+
+
+class _DecPrenet(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.fc1, self.fc2, self.proj = nn.Linear(c.n_mels, c.d_prenet), nn.Linear(c.d_prenet, c.d_prenet), nn.Linear(c.d_prenet, c.d_model)
+
+
+class _Postnet(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        ch = [c.n_mels] + [c.postnet_channels] * (c.postnet_layers - 1) + [c.n_mels]
+        self.convs = nn.ModuleList(_ConvBN(ch[i], ch[i + 1], c.conv_kernel, c.bn_eps) for i in range(c.postnet_layers))
+
+
+class _Stack(nn.Module):
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+
+
+class TransformerTTS(nn.Module):
+    """forward(): teacher-forced (eval-mode arithmetic); inference(): greedy AR over a KV cache.
+
+    Parameters live on the host (the packed bf16 copies the kernels read are owned by the C handle);
+    call `load_state_dict` then use the module -- weights are (re)packed lazily on first use."""
+
+    def __init__(self, cfg: Optional[TTSConfig] = None, device: int = 0):
+        super().__init__()
+        self.cfg = c = cfg or TTSConfig()
+        self.enc_prenet = _EncPrenet(c)
+        self.enc_alpha = nn.Parameter(torch.ones(()))
+        self.dec_alpha = nn.Parameter(torch.ones(()))
+        self.encoder = _Stack(_EncLayer(c) for _ in range(c.n_enc_layers))
+        self.dec_prenet = _DecPrenet(c)
+        self.decoder = _Stack(_DecLayer(c) for _ in range(c.n_dec_layers))
+        self.mel_linear = nn.Linear(c.d_model, c.n_mels)
+        self.stop_linear = nn.Linear(c.d_model, 1)
+        self.postnet = _Postnet(c)
+        self._device_index = device
+        self._lib = None
+        self._handle = C.c_void_p()
+        self._dirty = True
+        self._persistent = True
+        self._ws = None
+        self._ws_key = None
+        self.eval()
+
+    # ------------------------------------------------------------------ plumbing
+    def _ensure_handle(self):
+        if self._lib is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("transformer_tacotron2_b200 needs a B200 (sm_100a) GPU; there is no CPU fallback")
+            self._lib = _lib.load()
+            c = self.cfg
+            cc = _lib.TtsConfig(C.sizeof(_lib.TtsConfig), c.n_vocab, c.d_model, c.n_heads, c.n_enc_layers, c.n_dec_layers,
+                                c.d_ff, c.n_mels, c.d_prenet, c.enc_conv_layers, c.conv_kernel, c.postnet_channels,
+                                c.postnet_layers, c.max_pos, c.ln_eps, c.bn_eps)
+            rc = self._lib.tts_create(C.byref(cc), self._device_index, C.byref(self._handle))
+            if rc != 0:
+                raise _lib.TtsError(f"tts_create failed ({rc}): no sm_100 device {self._device_index}?")
+        return self._lib
+
+    def _check(self, rc, what):
+        _lib.check(self._lib, self._handle, rc, what)
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._dirty = True
+        return out
+
+    def set_option(self, key: str, value: int):
+        lib = self._ensure_handle()
+        self._check(lib.tts_set_option(self._handle, key.encode(), int(value)), "tts_set_option")
+        if key == "decode_persistent":
+            self._persistent = bool(value)
+
+    def sync_weights(self):
+        """Push the module's parameters through tts_load_weight / tts_finalize_weights."""
+        lib = self._ensure_handle()
+        if not self._dirty:
+            return
+        for name, t in self.state_dict().items():
+            if not t.is_floating_point():
+                continue                                  # num_batches_tracked
+            t = t.detach().to("cpu", torch.float32).contiguous()
+            self._check(lib.tts_load_weight(self._handle, name.encode(), C.c_void_p(t.data_ptr()), t.numel()), f"tts_load_weight({name})")
+        self._check(lib.tts_finalize_weights(self._handle), "tts_finalize_weights")
+        self._dirty = False
+
+    def _workspace(self, B, S, T):
+        lib = self._ensure_handle()
+        key = (B, S, T)
+        if self._ws_key != key:
+            n = lib.tts_workspace_bytes(self._handle, B, S, T)
+            if n == 0:
+                raise _lib.TtsError("tts_workspace_bytes returned 0 (bad shape)")
+            self._ws = None
+            self._ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._ws_key = key
+        return self._ws
+
+    @property
+    def device(self):
+        return torch.device("cuda", self._device_index)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def __del__(self):
+        try:
+            if self._lib is not None and self._handle:
+                self._lib.tts_destroy(self._handle)
+        except Exception:
+            pass
+
+    @staticmethod
+    def _utt_offset(utt_ids, B, utt_offset):
+        if utt_ids is None:
+            return int(utt_offset)
+        ids = [int(v) for v in utt_ids]
+        if ids != list(range(ids[0], ids[0] + B)):
+            raise ValueError("utt_ids must be a contiguous range (the C ABI takes the id of utterance 0)")
+        return ids[0]
+
+    # ------------------------------------------------------------------ teacher-forced
+    @torch.no_grad()
+    def forward(self, phonemes, phoneme_lens, mels, mel_lens, seed: int = 0, utt_ids=None, utt_offset: int = 0
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """phonemes [B,S] i64, phoneme_lens [B], mels [B,T,80] f32, mel_lens [B]
+        -> mel_before [B,T,80], mel_after [B,T,80], stop_logits [B,T]  (on the GPU, zero past mel_lens)."""
+        if self.training:
+            raise NotImplementedError("training-mode forward/backward is not built yet (SURVEY.md 8(f)); use .eval()")
+        lib = self._ensure_handle()
+        self.sync_weights()
+        dev = self.device
+        B, S = phonemes.shape
+        T = mels.shape[1]
+        ph = phonemes.to(dev, torch.int64).contiguous()
+        pl = phoneme_lens.to(dev, torch.int32).contiguous()
+        ml = mel_lens.to(dev, torch.int32).contiguous()
+        m = mels.to(dev, torch.float32).contiguous()
+        ws = self._workspace(B, S, T)
+        mb = torch.empty(B, T, 80, device=dev); ma = torch.empty(B, T, 80, device=dev); st = torch.empty(B, T, device=dev)
+        rc = lib.tts_forward(self._handle, ws.data_ptr(), ph.data_ptr(), pl.data_ptr(), m.data_ptr(), ml.data_ptr(), B, S, T,
+                             int(seed), self._utt_offset(utt_ids, B, utt_offset), mb.data_ptr(), ma.data_ptr(), st.data_ptr(), self._stream())
+        self._check(rc, "tts_forward")
+        return mb, ma, st
+
+    # ------------------------------------------------------------------ greedy AR
+    @torch.no_grad()
+    def inference(self, phonemes, phoneme_lens, max_len: int = 800, seed: int = 0, utt_ids=None, utt_offset: int = 0,
+                  return_before: bool = False):
+        """-> mel_after [B,Tout,80], mel_lens [B] i32, stop_logits [B,Tout].
+
+        CPU tensors in -> the whole call runs through tts_infer_host (H2D, encoder, decode loop,
+        postnet, D2H) and CPU tensors come back.  CUDA tensors in -> device-resident pipeline
+        (tts_encode / tts_decode_* ), CUDA tensors out."""
+        lib = self._ensure_handle()
+        self.sync_weights()
+        B, S = phonemes.shape
+        u0 = self._utt_offset(utt_ids, B, utt_offset)
+        ws = self._workspace(B, S, max_len)
+        if not phonemes.is_cuda and not return_before:
+            ph = phonemes.to(torch.int64).contiguous()
+            pl = phoneme_lens.to(torch.int32).contiguous()
+            ma = torch.empty(B, max_len, 80).pin_memory(); st = torch.empty(B, max_len).pin_memory()
+            ml = torch.empty(B, dtype=torch.int32).pin_memory()
+            tout = C.c_int(0)
+            rc = lib.tts_infer_host(self._handle, ws.data_ptr(), ph.data_ptr(), pl.data_ptr(), B, S, int(max_len), int(seed), u0,
+                                    ma.data_ptr(), ml.data_ptr(), st.data_ptr(), C.byref(tout), self._stream())
+            self._check(rc, "tts_infer_host")
+            T = tout.value
+            return (ma.view(-1)[: B * T * 80].view(B, T, 80).clone(), ml.clone(), st.view(-1)[: B * T].view(B, T).clone())
+        dev = self.device
+        ph = phonemes.to(dev, torch.int64).contiguous()
+        pl = phoneme_lens.to(dev, torch.int32).contiguous()
+        stream = self._stream()
+        self._check(lib.tts_decode_begin(self._handle, ws.data_ptr(), B, S, int(max_len), int(seed), u0, stream), "tts_decode_begin")
+        self._check(lib.tts_encode(self._handle, ws.data_ptr(), ph.data_ptr(), pl.data_ptr(), B, S, int(max_len), None, stream), "tts_encode")
+        td, nf = C.c_int(0), C.c_int(0)
+        chunk = int(max_len) if self._persistent else 16   # the persistent kernel stops itself on the device
+        while True:
+            self._check(lib.tts_decode_steps(self._handle, ws.data_ptr(), chunk, stream), "tts_decode_steps")
+            self._check(lib.tts_decode_status(self._handle, ws.data_ptr(), C.byref(td), C.byref(nf), stream), "tts_decode_status")
+            if nf.value >= B or td.value >= max_len:
+                break
+        T = td.value
+        ma = torch.empty(B, T, 80, device=dev); st = torch.empty(B, T, device=dev)
+        ml = torch.empty(B, dtype=torch.int32, device=dev)
+        mb = torch.empty(B, T, 80, device=dev) if return_before else None
+        rc = lib.tts_decode_end(self._handle, ws.data_ptr(), T, ma.data_ptr(), ml.data_ptr(), st.data_ptr(),
+                                mb.data_ptr() if return_before else None, stream)
+        self._check(rc, "tts_decode_end")
+        if not self._persistent and nf.value >= B:         # per-phase launches overshoot in chunks of 16 steps
+            T = int(ml.max())
+            ma, st = ma[:, :T].contiguous(), st[:, :T].contiguous()
+            mb = mb[:, :T].contiguous() if return_before else None
+        if return_before:
+            return ma, ml, st, mb
+        return ma, ml, st
+
+    @torch.no_grad()
+    def encode(self, phonemes, phoneme_lens, T: Optional[int] = None) -> torch.Tensor:
+        """Encoder output ("memory") [B,S,512] fp32 on the GPU (bf16 values widened)."""
+        lib = self._ensure_handle()
+        self.sync_weights()
+        dev = self.device
+        B, S = phonemes.shape
+        T = int(T or S)
+        ws = self._workspace(B, S, T)
+        ph = phonemes.to(dev, torch.int64).contiguous()
+        pl = phoneme_lens.to(dev, torch.int32).contiguous()
+        mem = torch.empty(B, S, 512, device=dev)
+        self._check(lib.tts_encode(self._handle, ws.data_ptr(), ph.data_ptr(), pl.data_ptr(), B, S, T, mem.data_ptr(), self._stream()), "tts_encode")
+        return mem

@@ -53,6 +53,8 @@ int tts_destroy(TtsHandle* h);
 const char* tts_last_error_string(TtsHandle* h);
 /* Library / build identification ("tts_b200 <version> sm_100a"). */
 const char* tts_version(void);
+/* Kernel launches issued by the library since it was loaded (bench.py: gpu_launches). */
+unsigned long long tts_launch_count(void);
 
 /* ---- weights: nn.Module.load_state_dict (same keys as the oracle's state_dict) --------------- */
 /* Stage one fp32 tensor (HOST pointer, `numel` elements, C-contiguous) under its state_dict key. */

@@ -296,6 +296,37 @@ class TransformerTTS(nn.Module):
         mel_after = (mel_before + self._postnet(mel_before, mel_lens, seed, b_ids)) * tm[..., None]
         return mel_before, mel_after, stop_logits
 
+    # ------------------------------------------------------------------ one AR step over the KV cache
+    @torch.no_grad()
+    def init_decode_state(self, memory, phoneme_lens, max_len: int):
+        """Hoisted cross-K/V projections + empty self-attention caches [B,H,max_len,64] per layer."""
+        c = self.cfg
+        B, S, _ = memory.shape
+        H, dh = c.n_heads, c.d_model // c.n_heads
+        layers = self.decoder.layers
+        return dict(
+            cross_mask=length_mask(phoneme_lens, S)[:, None, None, :],
+            ck=[l.cross_attn.split(l.cross_attn.wk(memory)) for l in layers],
+            cv=[l.cross_attn.split(l.cross_attn.wv(memory)) for l in layers],
+            sk=[torch.zeros(B, H, max_len, dh) for _ in layers],
+            sv=[torch.zeros(B, H, max_len, dh) for _ in layers])
+
+    @torch.no_grad()
+    def decode_step(self, state, frame, t: int, seed: int, b_ids):
+        """frame [B,1,80] (previous mel_before frame, fp32; zeros at t = 0) -> (frame_t [B,1,80], stop logit [B])."""
+        x = self._dec_prenet(frame, seed, np.array([t]), b_ids) + self.dec_alpha * self.pe[t][None, None]
+        for l, layer in enumerate(self.decoder.layers):
+            sa, sk, sv = layer.self_attn, state["sk"][l], state["sv"][l]
+            sk[:, :, t] = sa.split(sa.wk(x))[:, :, 0]
+            sv[:, :, t] = sa.split(sa.wv(x))[:, :, 0]
+            a = sa.attend(sa.split(sa.wq(x)), sk[:, :, : t + 1], sv[:, :, : t + 1], None)
+            x = layer.norm1(x + a)
+            ca = layer.cross_attn
+            a = ca.attend(ca.split(ca.wq(x)), state["ck"][l], state["cv"][l], state["cross_mask"])
+            x = layer.norm2(x + a)
+            x = layer.norm3(x + layer.ffn(x))
+        return self.mel_linear(x), self.stop_linear(x)[:, 0, 0]                 # fp32 feedback (P8)
+
     # ------------------------------------------------------------------ greedy AR with KV cache
     @torch.no_grad()
     def inference(self, phonemes, phoneme_lens, max_len: int = 800, seed: int = 0, utt_ids=None,
@@ -308,15 +339,9 @@ class TransformerTTS(nn.Module):
         assert not self.training, "inference() is an eval-mode path (prenet dropout stays on regardless)"
         c = self.cfg
         B, S = phonemes.shape
-        H, dh = c.n_heads, c.d_model // c.n_heads
         b_ids = np.arange(B) if utt_ids is None else np.asarray(utt_ids)
         memory = self.encode(phonemes, phoneme_lens, seed, utt_ids)
-        cross_mask = length_mask(phoneme_lens, S)[:, None, None, :]
-        layers = self.decoder.layers
-        ck = [l.cross_attn.split(l.cross_attn.wk(memory)) for l in layers]     # hoisted cross K/V
-        cv = [l.cross_attn.split(l.cross_attn.wv(memory)) for l in layers]
-        sk = [torch.zeros(B, H, max_len, dh) for _ in layers]
-        sv = [torch.zeros(B, H, max_len, dh) for _ in layers]
+        state = self.init_decode_state(memory, phoneme_lens, max_len)
         frame = torch.zeros(B, 1, c.n_mels)                                     # go frame
         mel_before = torch.zeros(B, max_len, c.n_mels)
         stop_logits = torch.zeros(B, max_len)
@@ -324,19 +349,7 @@ class TransformerTTS(nn.Module):
         finished = torch.zeros(B, dtype=torch.bool)
         n_steps = 0
         for t in range(max_len):
-            x = self._dec_prenet(frame, seed, np.array([t]), b_ids) + self.dec_alpha * self.pe[t][None, None]
-            for l, layer in enumerate(layers):
-                sa = layer.self_attn
-                sk[l][:, :, t] = sa.split(sa.wk(x))[:, :, 0]
-                sv[l][:, :, t] = sa.split(sa.wv(x))[:, :, 0]
-                a = sa.attend(sa.split(sa.wq(x)), sk[l][:, :, : t + 1], sv[l][:, :, : t + 1], None)
-                x = layer.norm1(x + a)
-                ca = layer.cross_attn
-                a = ca.attend(ca.split(ca.wq(x)), ck[l], cv[l], cross_mask)
-                x = layer.norm2(x + a)
-                x = layer.norm3(x + layer.ffn(x))
-            frame = self.mel_linear(x)                                          # fp32 feedback (P8)
-            logit = self.stop_linear(x)[:, 0, 0]
+            frame, logit = self.decode_step(state, frame, t, seed, b_ids)
             mel_before[:, t] = frame[:, 0]
             stop_logits[:, t] = logit
             n_steps = t + 1

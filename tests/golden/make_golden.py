@@ -17,7 +17,10 @@ from oracle import synthetic  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 FORWARD_CASE = dict(B=2, S=12, T=20, data_seed=201, seed=7, stop_bias=-8.0)
-INFER_CASE = dict(B=3, S=16, max_len=48, data_seed=202, seed=7, stop_bias=-0.45)
+# (data_seed, stop_bias) searched so that the oracle's minimum |stop logit| over the valid frames (the
+# "stop margin", 0.046 here) is well above the bf16 path's logit error (~0.006): only then is
+# "stop indices bit-exact" a meaningful requirement.
+INFER_CASE = dict(B=3, S=16, max_len=48, data_seed=212, seed=7, stop_bias=-0.505)
 
 
 def main():
@@ -38,7 +41,8 @@ def main():
     ma, lens, st, mb = m.inference(ph, pl, max_len=c["max_len"], seed=c["seed"], return_before=True)
     np.savez_compressed(os.path.join(HERE, "inference_small.npz"),
                         phonemes=ph.numpy(), phoneme_lens=pl.numpy(), mel_after=ma.numpy(), mel_before=mb.numpy(),
-                        mel_lens=lens.numpy(), stop_logits=st.numpy())
+                        mel_lens=lens.numpy(), stop_logits=st.numpy(), stop_bias=np.array(c["stop_bias"]),
+                        max_len=np.array(c["max_len"]), seed=np.array(c["seed"]))
     print("digest", digest, "lens", lens.tolist())
 
 

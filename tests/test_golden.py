@@ -24,10 +24,15 @@ def test_forward_matches_golden(oracle_model):
     assert np.allclose(st.numpy(), g["stop_logits"], atol=1e-4)
 
 
-def test_inference_matches_golden(oracle_model_stopping):
+def test_inference_matches_golden():
     g = np.load(os.path.join(GOLD, "inference_small.npz"))
-    ma, lens, st = oracle_model_stopping.inference(torch.from_numpy(g["phonemes"]),
+    model = synthetic.make_model(stop_bias=float(g["stop_bias"]))
+    ma, lens, st = model.inference(torch.from_numpy(g["phonemes"]),
                                                    torch.from_numpy(g["phoneme_lens"]), max_len=48, seed=7)
     assert lens.tolist() == g["mel_lens"].tolist()
     assert np.allclose(ma.numpy(), g["mel_after"], atol=2e-4)
     assert np.allclose(st.numpy(), g["stop_logits"], atol=2e-4)
+    assert len(set(lens.tolist())) == 3 and int(lens.max()) < 48          # ragged stops, all before max_len
+    T = st.shape[1]
+    valid = torch.arange(T)[None, :] < lens[:, None]
+    assert float(st.abs()[valid].min()) > 0.04                             # the searched stop margin

@@ -57,7 +57,8 @@ def test_conv5(lib, B, T, Cin, Cout):
     ref = torch.tanh(ref) * m[..., None]
     Wp = Wt.permute(2, 0, 1).contiguous().cuda()           # [5][Cout][Cin]
     Xd = Xm.to(torch.bfloat16).cuda(); Y = torch.empty(B, T, Cout, device="cuda")
-    rc = lib.tts_k_conv5(_p(Xd), _p(Wp), _p(bias.cuda()), _p(lens.cuda()), _p(Y), B, T, Cin, Cout, 2, _stream())
+    bias_d, lens_d = bias.cuda(), lens.cuda()               # keep every device buffer alive across the call
+    rc = lib.tts_k_conv5(_p(Xd), _p(Wp), _p(bias_d), _p(lens_d), _p(Y), B, T, Cin, Cout, 2, _stream())
     assert rc == 0
     torch.cuda.synchronize()
     assert torch.allclose(Y.cpu(), ref, atol=3e-3, rtol=3e-3), float((Y.cpu() - ref).abs().max())
@@ -81,14 +82,12 @@ def test_attention(lib, B, Lq, Lk, causal):
     s = s.masked_fill(~mask, float("-inf"))
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, Lq, H * 64)
     O = torch.empty(B, Lq, H * 64, dtype=torch.bfloat16, device="cuda")
-    rc = lib.tts_k_attention(_p(Q.cuda()), _p(K.cuda()), _p(V.cuda()), _p(O), _p(klens.cuda()), B, H, Lq, Lk, causal, _stream())
+    Qd, Kd, Vd, kl = Q.cuda(), K.cuda(), V.cuda(), klens.cuda()
+    rc = lib.tts_k_attention(_p(Qd), _p(Kd), _p(Vd), _p(O), _p(kl), B, H, Lq, Lk, causal, _stream())
     assert rc == 0
     torch.cuda.synchronize()
     got = O.float().cpu()
-    rows_ok = torch.ones(B, Lq, dtype=torch.bool)
-    if causal:                                              # rows whose every key is masked are undefined in the reference
-        rows_ok = torch.ones(B, Lq, dtype=torch.bool)
-    assert torch.allclose(got[rows_ok], ref[rows_ok], atol=2e-2, rtol=2e-2), float((got - ref).abs().max())
+    assert torch.allclose(got, ref, atol=2e-2, rtol=2e-2), float((got - ref).abs().max())
 
 
 def test_layernorm(lib):
@@ -96,7 +95,8 @@ def test_layernorm(lib):
     X = torch.randn(333, 512, generator=g) * 3 + 1
     gam, bet = torch.randn(512, generator=g), torch.randn(512, generator=g)
     Y = torch.empty(333, 512, dtype=torch.bfloat16, device="cuda")
-    rc = lib.tts_k_layernorm(_p(X.cuda()), _p(gam.cuda()), _p(bet.cuda()), _p(Y), 333, 1e-5, _stream())
+    Xd, gd, bd = X.cuda(), gam.cuda(), bet.cuda()
+    rc = lib.tts_k_layernorm(_p(Xd), _p(gd), _p(bd), _p(Y), 333, 1e-5, _stream())
     assert rc == 0
     ref = torch.nn.functional.layer_norm(X, (512,), gam, bet, 1e-5)
     torch.cuda.synchronize()

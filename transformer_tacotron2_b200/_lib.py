@@ -23,6 +23,7 @@ _P, _I, _I64, _U64, _SZ = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_size_t
 # name -> (restype, argtypes); every symbol include/tts_b200.h declares
 SIGNATURES = {
     "tts_version": (C.c_char_p, []),
+    "tts_launch_count": (C.c_ulonglong, []),
     "tts_create": (_I, [C.POINTER(TtsConfig), _I, C.POINTER(_P)]),
     "tts_destroy": (_I, [_P]),
     "tts_last_error_string": (C.c_char_p, [_P]),

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(128) flash_attn_fwd_kernel(const AttnParams p)
 inline cudaError_t launch_flash_attn(const AttnParams& p, cudaStream_t stream) {
     dim3 grid((p.Lq + FA_BM - 1) / FA_BM, p.H, p.B);
     flash_attn_fwd_kernel<<<grid, 128, 0, stream>>>(p);
+    ++launch_counter();
     return cudaGetLastError();
 }
 

@@ -12,6 +12,9 @@ typedef __nv_bfloat16 bf16;
 
 namespace tts {
 
+// Kernel launches issued by this library since load (bench.py reports it as gpu_launches).
+inline unsigned long long& launch_counter() { static unsigned long long n = 0; return n; }
+
 constexpr int kDModel = 512;     // the base model is the only model on this path
 constexpr int kHeads = 8;
 constexpr int kDHead = 64;

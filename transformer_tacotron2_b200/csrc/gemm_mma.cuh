@@ -182,6 +182,7 @@ inline cudaError_t launch_gemm(const GemmParams& p, cudaStream_t stream) {
     }
     dim3 grid((p.N + GB_N - 1) / GB_N, (p.M + GB_M - 1) / GB_M);
     gemm_mma_kernel<<<grid, 256, G_SMEM_BYTES, stream>>>(p);
+    ++launch_counter();
     return cudaGetLastError();
 }
 

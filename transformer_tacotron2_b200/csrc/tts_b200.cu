@@ -103,6 +103,8 @@ template <typename T> static inline T* wsp(void* ws, size_t off) { return reinte
 // ------------------------------------------------------------------------------------------------
 extern "C" const char* tts_version(void) { return "tts_b200 0.1 sm_100a"; }
 
+extern "C" unsigned long long tts_launch_count(void) { return launch_counter(); }
+
 extern "C" const char* tts_last_error_string(TtsHandle* h) { return h ? h->err.c_str() : "null handle"; }
 
 extern "C" int tts_create(const TtsConfig* cfg, int device, TtsHandle** out) {
@@ -358,6 +360,7 @@ AttnParams ap_packed(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16*
 }
 cudaError_t layernorm(const float* x, const float* g, const float* b, bf16* o16, float* o32, int M, float eps, cudaStream_t st) {
     layernorm512_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, g, b, o16, o32, M, eps);
+    ++launch_counter();
     return cudaGetLastError();
 }
 }  // namespace
@@ -370,6 +373,7 @@ static int run_encoder(TtsHandle* h, void* ws, const Ws& L, const int64_t* ph, c
     bf16 *x = wsp<bf16>(ws, L.x), *x2 = wsp<bf16>(ws, L.x2), *wide = wsp<bf16>(ws, L.wide), *a = wsp<bf16>(ws, L.a);
     float* y = wsp<float>(ws, L.y);
     embed_kernel<<<(M + 3) / 4, 256, 0, st>>>(ph, plens, h->embed, x, B, S, h->cfg.n_vocab);
+    ++launch_counter();
     CKL(cudaGetLastError());
     for (int i = 0; i < 3; ++i) {                                      // conv k5 + folded BN + ReLU + length mask
         GemmParams p = gp(x, 512, h->enc_conv_w[i], 512, M, 512, 512);
@@ -442,6 +446,7 @@ extern "C" int tts_encode(TtsHandle* h, void* ws, const int64_t* phonemes, const
     if (memory_out) {
         size_t n = (size_t)B * S * 512;
         bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(wsp<bf16>(ws, L.x), memory_out, n);
+        ++launch_counter();
         CK(cudaGetLastError());
     }
     return 0;
@@ -469,6 +474,7 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
     const int P = B * kHeads;
     init_decode_state_kernel<<<(std::max(P, 4) + 255) / 256, 256, 0, st>>>(wsp<int>(ws, L.lens), wsp<int>(ws, L.finished),
                                                                           wsp<int>(ws, L.scalars), wsp<unsigned>(ws, L.part_cnt), B, max_len, P);
+    ++launch_counter();
     CK(cudaGetLastError());
 
     float *xres = wsp<float>(ws, L.d_xres), *y = wsp<float>(ws, L.d_y), *q = wsp<float>(ws, L.d_q);
@@ -537,10 +543,12 @@ extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* strea
         int t0 = h->dec_t, ns = n_steps, pb = 0, pe = p.n_phases, pers = 1;
         void* args[] = {&p, &t0, &ns, &pb, &pe, &pers};
         CK(cudaLaunchCooperativeKernel((void*)decode_kernel, dim3(grid), dim3(kDecThreads), args, kDecSmemBytes, st));
+        ++launch_counter();
     } else {
         for (int s = 0; s < n_steps; ++s)
             for (int phs = 0; phs < p.n_phases; ++phs) {
                 decode_kernel<<<grid, kDecThreads, kDecSmemBytes, st>>>(p, h->dec_t + s, 1, phs, phs + 1, 0);
+                ++launch_counter();
                 CK(cudaGetLastError());
             }
         int td = h->dec_t + n_steps;
@@ -577,10 +585,12 @@ extern "C" int tts_decode_end(TtsHandle* h, void* ws, int T_out, float* mel_afte
     const int n = B * T_out * 24;
     mel_to_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(wsp<float>(ws, L.mel_before), h->dec_T, lens, 0,
                                                         wsp<bf16>(ws, L.mel16), wsp<float>(ws, L.mel32), B, T_out);
+    ++launch_counter();
     CK(cudaGetLastError());
     if (stop_logits || mel_lens) {
         float* so = stop_logits ? stop_logits : wsp<float>(ws, L.y);
         finalize_stop_kernel<<<(std::max(B * T_out, B) + 255) / 256, 256, 0, st>>>(wsp<float>(ws, L.stop_logits), h->dec_T, lens, so, mel_lens, B, T_out);
+        ++launch_counter();
         CK(cudaGetLastError());
     }
     if (mel_before) CK(cudaMemcpyAsync(mel_before, wsp<float>(ws, L.mel32), (size_t)B * T_out * 80 * 4, cudaMemcpyDeviceToDevice, st));
@@ -651,6 +661,7 @@ extern "C" int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, cons
     {   // P8: shift right, zero go-frame
         const int n = M * 24;
         mel_to_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(mels, T, mel_lens, 1, mel16, nullptr, B, T);
+        ++launch_counter();
         CK(cudaGetLastError());
     }
     {   // decoder prenet: dropout ALWAYS on (P7), masks keyed by (site, t, global utterance id)
@@ -698,6 +709,7 @@ extern "C" int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, cons
     {
         const int n = M * 24;
         mel_to_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(mel_before, T, mel_lens, 0, mel16, wsp<float>(ws, L.mel32), B, T);
+        ++launch_counter();
         CK(cudaGetLastError());
     }
     return run_postnet(h, ws, L, mel_lens, B, T, mel_after, st);
@@ -734,5 +746,6 @@ extern "C" int tts_k_philox_bits(uint64_t seed, int site, int T, int B, int C, i
     if (!out || T <= 0 || B <= 0 || C <= 0) return TTS_E_ARG;
     const int n = T * B * C;
     philox_bits_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seed, site, T, B, C, utt_offset, out);
+    ++launch_counter();
     return (int)cudaGetLastError();
 }

@@ -130,6 +130,8 @@ class TransformerTTS(nn.Module):
         self._handle = C.c_void_p()
         self._dirty = True
         self._persistent = True
+        self.profile_events = False      # bench.py: CUDA-event time of the decode loop per inference()
+        self.decode_ms = []
         self._ws = None
         self._ws_key = None
         self.eval()
@@ -268,11 +270,18 @@ class TransformerTTS(nn.Module):
         self._check(lib.tts_encode(self._handle, ws.data_ptr(), ph.data_ptr(), pl.data_ptr(), B, S, int(max_len), None, stream), "tts_encode")
         td, nf = C.c_int(0), C.c_int(0)
         chunk = int(max_len) if self._persistent else 16   # the persistent kernel stops itself on the device
+        if self.profile_events:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(dev))
         while True:
             self._check(lib.tts_decode_steps(self._handle, ws.data_ptr(), chunk, stream), "tts_decode_steps")
+            if self.profile_events:
+                ev1.record(torch.cuda.current_stream(dev))
             self._check(lib.tts_decode_status(self._handle, ws.data_ptr(), C.byref(td), C.byref(nf), stream), "tts_decode_status")
             if nf.value >= B or td.value >= max_len:
                 break
+        if self.profile_events:
+            self.decode_ms.append(ev0.elapsed_time(ev1))
         T = td.value
         ma = torch.empty(B, T, 80, device=dev); st = torch.empty(B, T, device=dev)
         ml = torch.empty(B, dtype=torch.int32, device=dev)

@@ -64,7 +64,8 @@ int tts_load_weight(TtsHandle* h, const char* name, const float* host_data, int6
 int tts_finalize_weights(TtsHandle* h);
 
 /* ---- options ---------------------------------------------------------------------------------- */
-/* "decode_persistent": 1 (default) one cooperative persistent kernel for the AR loop; 0 one launch per phase. */
+/* "decode_persistent": 1 (default) one cooperative persistent kernel for the AR loop; 0 one launch per phase.
+ * "decode_timestamps": 1 record per-phase timestamps (see tts_debug_phase_timestamps). */
 int tts_set_option(TtsHandle* h, const char* key, int64_t value);
 
 /* ---- workspace ---------------------------------------------------------------------------------- */
@@ -101,6 +102,10 @@ int tts_infer_host(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_
 int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* phoneme_lens,
                 const float* mels, const int32_t* mel_lens, int B, int S, int T, uint64_t seed, int utt_offset,
                 float* mel_before, float* mel_after, float* stop_logits, void* stream);
+
+/* Profiling aid: with option "decode_timestamps" = 1 the persistent decode kernel stamps %globaltimer
+ * after every phase; this copies [n_steps][n_phases] stamps (ns) to the host and returns n_phases. [sync] */
+int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long long* out, int n_steps, void* stream);
 
 /* ---- per-kernel entry points (tests/test_gpu_kernels.py; not part of the drop-in surface) ---- */
 /* C[M][N] = act(A[M][K] . W[N][K]^T + bias) ; bf16 in, fp32 out; act 0 none / 1 relu / 2 tanh. */

@@ -1,0 +1,44 @@
+"""Per-phase timing of the persistent decode kernel from in-kernel %globaltimer stamps.
+Usage (GPU box): python scripts/profile_decode.py [B] [T] [S]   -> prints a table, writes gpurun_out/phase_times.json"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import synthetic_state_dict, synthetic_inputs, decode_bytes  # noqa: E402
+from transformer_tacotron2_b200 import TransformerTTS  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 800
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+names = ["fc1", "fc2", "proj"] + [f"L{l}.{n}" for l in range(6) for n in ("qkv", "self_attn", "o", "cq", "cross_attn", "o2", "ffn1", "ffn2")] + ["head"]
+m = TransformerTTS()
+m.load_state_dict(synthetic_state_dict().state_dict())
+m.set_option("decode_timestamps", 1)
+ph, pl = synthetic_inputs(B, S, 103)
+ph, pl = ph.cuda(), pl.cuda()
+for _ in range(2):
+    m.inference(ph, pl, max_len=T, seed=7)
+ts = m.phase_timestamps(T).double()                    # [T, 52] ns, stamp taken after each phase's barrier
+flat = ts.view(-1)
+d = (flat[1:] - flat[:-1]).view(-1)
+d = torch.cat([d[:1] * 0, d]).view(T, len(names)) / 1e3   # us per phase (first phase of step 0 unknown -> 0)
+step_us = d.sum(1)
+groups = {}
+for i, n in enumerate(names):
+    key = n.split(".")[-1]
+    groups.setdefault(key, []).append(i)
+out = {"B": B, "T": T, "S": S, "us_per_step_mean": float(step_us[1:].mean()), "windows": {}}
+for lo, hi in ((1, 50), (T // 2 - 25, T // 2 + 25), (T - 50, T)):
+    w = d[lo:hi]
+    row = {k: float(w[:, idx].mean()) for k, idx in groups.items()}      # mean us per phase instance
+    tot = {k: float(w[:, idx].sum(1).mean()) for k, idx in groups.items()}  # us per step for the whole group
+    out["windows"][f"{lo}-{hi}"] = {"per_phase_us": row, "per_step_us": tot, "step_us": float(w.sum(1).mean())}
+    print(f"steps {lo}-{hi}: {w.sum(1).mean():.1f} us/step")
+    for k in row:
+        print(f"   {k:11s} {row[k]:7.2f} us/phase x{len(groups[k]):2d} = {tot[k]:7.1f} us/step")
+print("mean us/step", out["us_per_step_mean"], " roofline us/step", decode_bytes(B, T, S) / T / 6468.6e3)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/phase_times.json", "w"), indent=1)

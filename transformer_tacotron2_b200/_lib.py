@@ -38,6 +38,7 @@ SIGNATURES = {
     "tts_decode_end": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "tts_infer_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _U64, _I, _P, _P, _P, C.POINTER(_I), _P]),
     "tts_forward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _U64, _I, _P, _P, _P, _P]),
+    "tts_debug_phase_timestamps": (_I, [_P, _P, _P, _I, _P]),
     "tts_k_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "tts_k_conv5": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "tts_k_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

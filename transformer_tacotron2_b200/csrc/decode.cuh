@@ -57,6 +57,7 @@ struct DecodeParams {
     int* lens; int* finished; int* n_finished; int* t_done;
     float* part_acc; float* part_ml; unsigned* part_cnt;
     unsigned* barrier;
+    unsigned long long* ts;        // optional [steps][n_phases] globaltimer stamps (debug / profiling)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -149,28 +150,38 @@ __device__ __noinline__ void dec_gemm_item(const PhaseDesc& d, const DecodeParam
             uint2 u = make_uint2(pack_bf16x2(v[i * 4], v[i * 4 + 1]), pack_bf16x2(v[i * 4 + 2], v[i * 4 + 3]));
             *reinterpret_cast<uint2*>(As + warp * lds + i * 128 + lane * 4) = u;
         }
-    } else if (d.a_kind == A_BF16) {
+    } else if (d.a_kind == A_BF16) {                  // cp.async.cg: L2-coherent, all chunks in flight at once
         const int cpr = K >> 3;                       // 16-byte chunks per row
         const bf16* src = reinterpret_cast<const bf16*>(d.a);
         for (int c = tid; c < 16 * cpr; c += kDecThreads) {
             const int r = c / cpr, ch = c - r * cpr, b = row0 + r;
-            uint4 u = make_uint4(0, 0, 0, 0);
-            if (b < p.B && ch * 8 < d.Kreal) u = ld_cg_u4(src + (size_t)b * d.lda + ch * 8);
-            *reinterpret_cast<uint4*>(As + r * lds + ch * 8) = u;
+            const bool ok = b < p.B && ch * 8 < d.Kreal;
+            cp_async_16(As + r * lds + ch * 8, src + (ok ? ((size_t)b * d.lda + ch * 8) : 0), ok);
         }
-    } else {                                          // A_F32 / A_FRAME: fp32 rows -> bf16
+        cp_async_commit();
+        cp_async_wait<0>();
+    } else {                                          // A_F32 / A_FRAME: fp32 rows -> bf16 (K <= 512: <= 4 chunks/thread)
         const int cpr = K >> 2;                       // float4 chunks per row
-        for (int c = tid; c < 16 * cpr; c += kDecThreads) {
+        float4 x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                 // issue every load before the first use
+            const int c = tid + i * kDecThreads;
             const int r = c / cpr, ch = c - r * cpr, b = row0 + r;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b < p.B && ch * 4 < d.Kreal) {
+            x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < 16 * cpr && b < p.B && ch * 4 < d.Kreal) {
                 if (d.a_kind == A_FRAME) {            // previous frame (fp32 feedback, P8); zero go-frame at t = 0
-                    if (t > 0) x = ld_cg_f4(p.mel_before + ((size_t)b * p.Tmax + (t - 1)) * 80 + ch * 4);
+                    if (t > 0) x[i] = ld_cg_f4(p.mel_before + ((size_t)b * p.Tmax + (t - 1)) * 80 + ch * 4);
                 } else {
-                    x = ld_cg_f4(reinterpret_cast<const float*>(d.a) + (size_t)b * d.lda + ch * 4);
+                    x[i] = ld_cg_f4(reinterpret_cast<const float*>(d.a) + (size_t)b * d.lda + ch * 4);
                 }
             }
-            *reinterpret_cast<uint2*>(As + r * lds + ch * 4) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = tid + i * kDecThreads;
+            const int r = c / cpr, ch = c - r * cpr;
+            if (c < 16 * cpr)
+                *reinterpret_cast<uint2*>(As + r * lds + ch * 4) = make_uint2(pack_bf16x2(x[i].x, x[i].y), pack_bf16x2(x[i].z, x[i].w));
         }
     }
     __syncthreads();
@@ -365,16 +376,14 @@ __device__ __noinline__ void dec_attn_phase(const PhaseDesc& d, const DecodePara
 
 // ------------------------------------------------------------------------------------------------
 TTS_D void grid_barrier(unsigned* bar, unsigned& target) {
-    __syncthreads();
+    __syncthreads();                                   // every thread's writes happen-before thread 0's release
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while (v < target);
-        __threadfence();
     }
     __syncthreads();
 }
@@ -391,7 +400,14 @@ decode_kernel(const DecodeParams p, int t0, int n_steps, int ph_begin, int ph_en
             const PhaseDesc& d = p.phases[ph];
             if (d.type == PH_GEMM) dec_gemm_phase(d, p, t, dec_smem);
             else dec_attn_phase(d, p, t);
-            if (persistent) grid_barrier(p.barrier, target);
+            if (persistent) {
+                grid_barrier(p.barrier, target);
+                if (p.ts && blockIdx.x == 0 && threadIdx.x == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+                    p.ts[(size_t)step * p.n_phases + ph] = now;
+                }
+            }
         }
         if (persistent) {
             if (blockIdx.x == 0 && threadIdx.x == 0) *p.t_done = t + 1;

@@ -27,7 +27,7 @@ struct TtsHandle {
     std::string err;
     std::map<std::string, std::vector<float>> staged;
     bool finalized = false;
-    int decode_persistent = 1;
+    int decode_persistent = 1, decode_timestamps = 0;
     unsigned char* arena = nullptr; size_t arena_bytes = 0;
     // ---- device weights (pointers into arena)
     bf16* embed = nullptr;
@@ -75,7 +75,7 @@ static inline uint16_t f2bf(float f) {                                // round-t
 struct Ws {
     size_t total = 0;
     size_t self_kv, cross_kv, mel_before, stop_logits, lens, finished, scalars, part_acc, part_ml, part_cnt, phases;
-    size_t d_xres, d_y, d_q, d_a, d_h, d_h1, d_h2;                    // decode-step activations
+    size_t d_xres, d_y, d_q, d_a, d_h, d_h1, d_h2, ts;                // decode-step activations, phase timestamps
     size_t x, x2, wide, a, y, mel16, mel32, ph, plens, mlens;         // sequence-parallel activations
     static Ws make(int B, int S, int T) {
         Ws w; size_t o = 0;
@@ -91,6 +91,7 @@ struct Ws {
         w.phases = take(64 * sizeof(PhaseDesc));
         w.d_xres = take(Bp * 512 * 4); w.d_y = take(Bp * 512 * 4); w.d_q = take(Bp * 512 * 4);
         w.d_a = take(Bp * 512 * 2); w.d_h = take(Bp * 2048 * 2); w.d_h1 = take(Bp * 256 * 2); w.d_h2 = take(Bp * 256 * 2);
+        w.ts = take((size_t)T * 64 * 8);
         w.x = take(M * 512 * 2); w.x2 = take(M * 512 * 2); w.wide = take(M * 2048 * 2); w.a = take(M * 512 * 2);
         w.y = take(M * 512 * 4); w.mel16 = take(M * 96 * 2); w.mel32 = take(M * 80 * 4);
         w.ph = take((size_t)B * S * 8); w.plens = take(B * 4); w.mlens = take(B * 4);
@@ -137,6 +138,7 @@ extern "C" int tts_destroy(TtsHandle* h) {
 extern "C" int tts_set_option(TtsHandle* h, const char* key, int64_t value) {
     if (!h || !key) return TTS_E_ARG;
     if (!strcmp(key, "decode_persistent")) { h->decode_persistent = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "decode_timestamps")) { h->decode_timestamps = value ? 1 : 0; return 0; }
     FAIL(TTS_E_ARG, std::string("unknown option ") + key);
 }
 
@@ -539,6 +541,7 @@ extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* strea
     DecodeParams p = h->dparams;
     const int grid = h->num_sms;
     if (h->decode_persistent) {
+        p.ts = h->decode_timestamps ? wsp<unsigned long long>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).ts) + (size_t)h->dec_t * p.n_phases : nullptr;
         CK(cudaMemsetAsync(p.barrier, 0, 4, st));
         int t0 = h->dec_t, ns = n_steps, pb = 0, pe = p.n_phases, pers = 1;
         void* args[] = {&p, &t0, &ns, &pb, &pe, &pers};
@@ -716,6 +719,16 @@ extern "C" int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// profiling aid: copy the per-phase globaltimer stamps of the persistent decode kernel to the host.
+extern "C" int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long long* out, int n_steps, void* stream) {
+    if (!h || !ws || !out || n_steps <= 0) return TTS_E_ARG;
+    if (!h->dec_active || n_steps > h->dec_T) FAIL(TTS_E_STATE, "no decode session / too many steps");
+    const Ws L = Ws::make(h->dec_B, h->dec_S, h->dec_T);
+    CK(cudaMemcpyAsync(out, wsp<unsigned long long>(ws, L.ts), (size_t)n_steps * h->dparams.n_phases * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return h->dparams.n_phases;
+}
+
 // per-kernel test entry points
 extern "C" int tts_k_gemm(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int act, void* stream) {
     if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || (K % 32) || (N % 128)) return TTS_E_ARG;

@@ -297,6 +297,14 @@ class TransformerTTS(nn.Module):
             return ma, ml, st, mb
         return ma, ml, st
 
+    def phase_timestamps(self, n_steps: int) -> torch.Tensor:
+        """[n_steps, n_phases] int64 ns stamps of the last persistent decode (option decode_timestamps = 1)."""
+        out = torch.zeros(n_steps, 64, dtype=torch.int64)
+        n = self._lib.tts_debug_phase_timestamps(self._handle, self._ws.data_ptr(), out.data_ptr(), n_steps, self._stream())
+        if n <= 0:
+            raise _lib.TtsError(f"tts_debug_phase_timestamps failed ({n})")
+        return out.view(-1)[: n_steps * n].view(n_steps, n).clone()
+
     @torch.no_grad()
     def encode(self, phonemes, phoneme_lens, T: Optional[int] = None) -> torch.Tensor:
         """Encoder output ("memory") [B,S,512] fp32 on the GPU (bf16 values widened)."""

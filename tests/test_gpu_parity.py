@@ -113,17 +113,57 @@ def test_inference_stopping_vs_oracle_and_golden(models):
     assert rel_l2(ga, torch.from_numpy(z["mel_after"])) < TOL_AR
 
 
-def test_persistent_equals_per_phase_launches(models):
-    """The cooperative persistent kernel and the one-launch-per-phase schedule run the same phase
+def test_grid_persistent_equals_per_phase_launches(models):
+    """The grid-barrier persistent kernel and the one-launch-per-phase schedule run the same phase
     code: results must be bit-identical."""
     from oracle import synthetic
     _, _, o, g = models
     ph, pl, _, _ = synthetic.make_inputs(5, 20, 8, 43, ragged=True)
-    a1, l1, s1 = (t.cpu() for t in g.inference(ph.cuda(), pl.cuda(), max_len=24, seed=3))
-    g2 = make_b200_model(o, persistent=False)
+    g1 = make_b200_model(o, persistent=True, cluster=False)
+    a1, l1, s1 = (t.cpu() for t in g1.inference(ph.cuda(), pl.cuda(), max_len=24, seed=3))
+    g2 = make_b200_model(o, persistent=False, cluster=False)
     a2, l2, s2 = (t.cpu() for t in g2.inference(ph.cuda(), pl.cuda(), max_len=24, seed=3))
     assert l1.tolist() == l2.tolist()
     assert torch.equal(a1, a2) and torch.equal(s1, s2)
+
+
+@pytest.mark.parametrize("B,S,T", [(1, 10, 20), (5, 33, 40), (8, 20, 150), (11, 24, 30), (20, 50, 64)])
+def test_cluster_kernel_vs_oracle_and_grid_kernel(models, B, S, T):
+    """The cluster-partitioned decode kernel (default) against the oracle and against the grid-barrier
+    kernel, across group shapes: a partial group, one full group, several clusters, ragged lengths, and
+    a KV length that spans more than one 128-row ring chunk."""
+    from oracle import synthetic
+    o, g, _, _ = models
+    ph, pl, _, _ = synthetic.make_inputs(B, S, 8, 50 + B, ragged=True)
+    ma, lens, st = o.inference(ph, pl, max_len=T, seed=7)
+    ga, gl, gs = (t.cpu() for t in g.inference(ph.cuda(), pl.cuda(), max_len=T, seed=7))
+    g2 = make_b200_model(o, persistent=True, cluster=False)
+    ha, hl, hs = (t.cpu() for t in g2.inference(ph.cuda(), pl.cuda(), max_len=T, seed=7))
+    print(f"cluster vs oracle rel-L2 {rel_l2(ga, ma):.4f} stop err {float((gs - st).abs().max()):.4f}; vs grid kernel {rel_l2(ga, ha):.4f}")
+    assert gl.tolist() == lens.tolist() == hl.tolist()
+    assert rel_l2(ga, ma) < TOL_AR and float((gs - st).abs().max()) < TOL_STOP
+    assert rel_l2(ga, ha) < TOL_AR
+
+
+def test_cluster_kernel_resume_in_chunks(models):
+    """tts_decode_steps may be called repeatedly (t0 > 0 resumes from the KV cache and the last frame)."""
+    import ctypes as C
+    from oracle import synthetic
+    o, g, _, _ = models
+    ph, pl, _, _ = synthetic.make_inputs(4, 18, 8, 61, ragged=True)
+    a1, l1, s1 = (t.cpu() for t in g.inference(ph.cuda(), pl.cuda(), max_len=20, seed=7))
+    lib, hnd = g._lib, g._handle
+    ws = g._workspace(4, 18, 20)
+    stream = g._stream()
+    phd, pld = ph.cuda(), pl.cuda().int()
+    assert lib.tts_decode_begin(hnd, ws.data_ptr(), 4, 18, 20, 7, 0, stream) == 0
+    assert lib.tts_encode(hnd, ws.data_ptr(), phd.data_ptr(), pld.data_ptr(), 4, 18, 20, None, stream) == 0
+    for n in (3, 1, 9, 7):
+        assert lib.tts_decode_steps(hnd, ws.data_ptr(), n, stream) == 0
+    ma = torch.empty(4, 20, 80, device="cuda"); st = torch.empty(4, 20, device="cuda"); ml = torch.empty(4, dtype=torch.int32, device="cuda")
+    assert lib.tts_decode_end(hnd, ws.data_ptr(), 20, ma.data_ptr(), ml.data_ptr(), st.data_ptr(), None, stream) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(ma.cpu(), a1) and torch.equal(st.cpu(), s1)
 
 
 def test_sharded_equals_unsharded_bitwise(models):

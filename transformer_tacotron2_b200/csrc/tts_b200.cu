@@ -17,6 +17,7 @@
 #include "attention_mma.cuh"
 #include "misc_kernels.cuh"
 #include "decode.cuh"
+#include "decode_cluster.cuh"
 
 using namespace tts;
 
@@ -28,6 +29,10 @@ struct TtsHandle {
     std::map<std::string, std::vector<float>> staged;
     bool finalized = false;
     int decode_persistent = 1, decode_timestamps = 0;
+    int decode_cluster = 1;                                           // 1: cluster-partitioned kernel when the device can co-schedule 16-CTA clusters
+    int cluster_ok = -1, max_clusters = 0;                            // probed lazily
+    unsigned char* cl_wpack = nullptr;                                // [16][CLW_RANK_BYTES] (own allocation)
+    ClusterParams cparams;
     unsigned char* arena = nullptr; size_t arena_bytes = 0;
     // ---- device weights (pointers into arena)
     bf16* embed = nullptr;
@@ -130,6 +135,7 @@ extern "C" int tts_destroy(TtsHandle* h) {
     if (!h) return TTS_E_ARG;
     cudaSetDevice(h->device);
     if (h->arena) cudaFree(h->arena);
+    if (h->cl_wpack) cudaFree(h->cl_wpack);
     if (h->h_status) cudaFreeHost(h->h_status);
     delete h;
     return 0;
@@ -139,6 +145,7 @@ extern "C" int tts_set_option(TtsHandle* h, const char* key, int64_t value) {
     if (!h || !key) return TTS_E_ARG;
     if (!strcmp(key, "decode_persistent")) { h->decode_persistent = value ? 1 : 0; return 0; }
     if (!strcmp(key, "decode_timestamps")) { h->decode_timestamps = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "decode_cluster")) { h->decode_cluster = value ? 1 : 0; return 0; }
     FAIL(TTS_E_ARG, std::string("unknown option ") + key);
 }
 
@@ -192,6 +199,31 @@ size_t pack_f32(Arena& ar, const float* v, size_t n, size_t npad = 0) {
     return off;
 }
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// One segment of a cluster rank's weight stream: `ntiles` tiles of 16 output rows (global row indices in
+// rows[], -1 = zero row) x KP k-pairs starting at k-pair kp_lo, blocks in [tile][kp] order; each
+// 16 x 32 block = 2 x (32 lanes x uint4) in mma.sync m16n8k16 A-fragment order (decode_cluster.cuh).
+void pack_cluster_segment(std::vector<unsigned char>& out, const float* w, int N, int K, const std::vector<int>& rows, int kp_lo, int KP) {
+    const int ntiles = (int)rows.size() / 16;
+    const size_t base = out.size();
+    out.resize(base + (size_t)ntiles * KP * 1024, 0);
+    auto at = [&](int row, int k) -> uint32_t { return (row >= 0 && row < N && k < K) ? f2bf(w[(size_t)row * K + k]) : 0; };
+    for (int ti = 0; ti < ntiles; ++ti)
+        for (int kp = 0; kp < KP; ++kp) {
+            uint32_t* blk = reinterpret_cast<uint32_t*>(out.data() + base + ((size_t)ti * KP + kp) * 1024);
+            for (int ks = 0; ks < 2; ++ks)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int g = lane >> 2, t4 = lane & 3, k0 = (kp_lo + kp) * 32 + ks * 16 + t4 * 2;
+                    const int r0 = rows[ti * 16 + g], r1 = rows[ti * 16 + g + 8];
+                    uint32_t* q = blk + (ks * 32 + lane) * 4;
+                    q[0] = at(r0, k0) | (at(r0, k0 + 1) << 16);
+                    q[1] = at(r1, k0) | (at(r1, k0 + 1) << 16);
+                    q[2] = at(r0, k0 + 8) | (at(r0, k0 + 9) << 16);
+                    q[3] = at(r1, k0 + 8) | (at(r1, k0 + 9) << 16);
+                }
+        }
+}
+std::vector<int> iota_rows(int lo, int n) { std::vector<int> r(n); for (int i = 0; i < n; ++i) r[i] = lo + i; return r; }
 }  // namespace
 
 extern "C" int tts_finalize_weights(TtsHandle* h) {
@@ -321,7 +353,46 @@ extern "C" int tts_finalize_weights(TtsHandle* h) {
             }
         bind(&h->pe, pack_f32(ar, pe.data(), pe.size()));
     }
+    // ---- per-rank weight streams of the cluster decode kernel (decode_cluster.cuh), in consumption order
+    std::vector<unsigned char> clw((size_t)CL_SIZE * CLW_RANK_BYTES);
+    {
+        GET(wf1, "dec_prenet.fc1.weight", (size_t)256 * 80); GET(wf2, "dec_prenet.fc2.weight", (size_t)256 * 256);
+        GET(wpj, "dec_prenet.proj.weight", (size_t)512 * 256);
+        GET(wm, "mel_linear.weight", (size_t)80 * D); GET(wsx, "stop_linear.weight", (size_t)D);
+        std::vector<float> whead((size_t)81 * D);
+        memcpy(whead.data(), wm, (size_t)80 * D * 4); memcpy(&whead[(size_t)80 * D], wsx, D * 4);
+        for (int rk = 0; rk < CL_SIZE; ++rk) {
+            std::vector<unsigned char> seg;
+            seg.reserve(CLW_RANK_BYTES);
+            pack_cluster_segment(seg, wf1, 256, 80, iota_rows(16 * rk, 16), 0, 3);
+            pack_cluster_segment(seg, wf2, 256, 256, iota_rows(16 * rk, 16), 0, 8);
+            pack_cluster_segment(seg, wpj, 512, 256, iota_rows(32 * rk, 32), 0, 8);
+            for (int l = 0; l < 6; ++l) {
+                const std::string p = "decoder.layers." + std::to_string(l);
+                if ((r = cat3(p + ".self_attn", w3, b3))) return r;
+                GET(wo, p + ".self_attn.wo.weight", (size_t)D * D); GET(wq2, p + ".cross_attn.wq.weight", (size_t)D * D);
+                GET(wo2, p + ".cross_attn.wo.weight", (size_t)D * D);
+                GET(w1, p + ".ffn.w1.weight", (size_t)F * D); GET(w2, p + ".ffn.w2.weight", (size_t)D * F);
+                std::vector<int> qrows(96);                       // 32 dims of q, k, v of head rk/2, half rk%2
+                for (int cc = 0; cc < 96; ++cc) qrows[cc] = (cc >> 5) * 512 + (rk >> 1) * 64 + (rk & 1) * 32 + (cc & 31);
+                pack_cluster_segment(seg, w3.data(), 3 * D, D, qrows, 0, 16);
+                pack_cluster_segment(seg, wo, D, D, iota_rows(32 * rk, 32), 0, 16);
+                pack_cluster_segment(seg, wq2, D, D, iota_rows(32 * rk, 32), 0, 16);
+                pack_cluster_segment(seg, wo2, D, D, iota_rows(32 * rk, 32), 0, 16);
+                pack_cluster_segment(seg, w1, F, D, iota_rows(128 * rk, 128), 0, 16);
+                pack_cluster_segment(seg, w2, D, F, iota_rows(0, 512), 4 * rk, 4);      // K-slice [128 rk, 128 rk + 128)
+            }
+            std::vector<int> hrows(16);
+            for (int i = 0; i < 16; ++i) hrows[i] = (rk < 6 && 16 * rk + i < 81) ? 16 * rk + i : -1;
+            pack_cluster_segment(seg, whead.data(), 81, D, hrows, 0, 16);
+            if (seg.size() != CLW_RANK_BYTES) FAIL(TTS_E_STATE, "cluster weight stream size mismatch");
+            memcpy(clw.data() + (size_t)rk * CLW_RANK_BYTES, seg.data(), CLW_RANK_BYTES);
+        }
+    }
 #undef GET
+    if (h->cl_wpack) { cudaFree(h->cl_wpack); h->cl_wpack = nullptr; }
+    CK(cudaMalloc(&h->cl_wpack, clw.size()));
+    CK(cudaMemcpy(h->cl_wpack, clw.data(), clw.size(), cudaMemcpyHostToDevice));
     if (h->arena) { cudaFree(h->arena); h->arena = nullptr; }
     h->arena_bytes = align_up(ar.host.size());
     CK(cudaMalloc(&h->arena, h->arena_bytes));
@@ -528,6 +599,31 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
     int* sc = wsp<int>(ws, L.scalars);
     p.n_finished = sc; p.t_done = sc + 1; p.barrier = reinterpret_cast<unsigned*>(sc + 2);
     p.part_acc = wsp<float>(ws, L.part_acc); p.part_ml = wsp<float>(ws, L.part_ml); p.part_cnt = wsp<unsigned>(ws, L.part_cnt);
+
+    ClusterParams& cp = h->cparams; memset(&cp, 0, sizeof(cp));
+    cp.B = B; cp.Tmax = max_len; cp.S = S; cp.ngroups = (B + CL_G - 1) / CL_G;
+    cp.seed = seed; cp.utt_offset = utt_offset; cp.dec_alpha = h->dec_alpha; cp.pe = h->pe;
+    cp.wpack = h->cl_wpack; cp.b_fc1 = h->pre_b1; cp.b_fc2 = h->pre_b2; cp.b_proj = h->pre_bp; cp.b_head = h->head_b;
+    for (int l = 0; l < 6; ++l) {
+        auto& W = h->dec[l];
+        cp.layer[l] = ClusterLayerParams{W.bqkv, W.bo, W.bq2, W.bo2, W.b1, W.b2, W.ln1g, W.ln1b, W.ln2g, W.ln2b, W.ln3g, W.ln3b};
+    }
+    cp.self_kv = skv; cp.cross_kv = ckv; cp.plens = plens;
+    cp.mel_before = p.mel_before; cp.stop_logits = p.stop_logits; cp.lens = p.lens; cp.finished = p.finished; cp.n_finished = p.n_finished;
+    if (h->cluster_ok < 0) {                                            // can this device co-schedule 16-CTA clusters of this kernel?
+        h->cluster_ok = 0;
+        if (cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+            cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES) == cudaSuccess) {
+            cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(CL_SIZE * 8); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES;
+            cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel, &cfg) == cudaSuccess && n > 0) { h->cluster_ok = 1; h->max_clusters = n; }
+        }
+        cudaGetLastError();
+    }
     return 0;
 }
 
@@ -540,7 +636,16 @@ extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* strea
     if (n_steps <= 0) return 0;
     DecodeParams p = h->dparams;
     const int grid = h->num_sms;
-    if (h->decode_persistent) {
+    if (h->decode_persistent && h->decode_cluster && h->cluster_ok == 1) {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        const int ncl = std::min(h->cparams.ngroups, h->max_clusters);
+        cfg.gridDim = dim3(CL_SIZE * ncl); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, decode_cluster_kernel, h->cparams, h->dec_t, n_steps));
+        ++launch_counter();
+    } else if (h->decode_persistent) {
         p.ts = h->decode_timestamps ? wsp<unsigned long long>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).ts) + (size_t)h->dec_t * p.n_phases : nullptr;
         CK(cudaMemsetAsync(p.barrier, 0, 4, st));
         int t0 = h->dec_t, ns = n_steps, pb = 0, pe = p.n_phases, pers = 1;
@@ -554,9 +659,6 @@ extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* strea
                 ++launch_counter();
                 CK(cudaGetLastError());
             }
-        int td = h->dec_t + n_steps;
-        CK(cudaMemcpyAsync(p.t_done, &td, 4, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
     }
     h->dec_t += n_steps;                                                // upper bound; tts_decode_status refines it
     return 0;
@@ -567,11 +669,18 @@ extern "C" int tts_decode_status(TtsHandle* h, void* ws, int* t_done, int* n_fin
     if (!h->dec_active) FAIL(TTS_E_STATE, "tts_decode_begin not called");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMemcpyAsync(h->h_status, h->dparams.n_finished, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_status, h->dparams.n_finished, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (n_finished) *n_finished = h->h_status[0];
-    if (t_done) *t_done = h->h_status[1];
-    if (h->h_status[0] >= h->dec_B) h->dec_t = h->h_status[1];        // early exit on the device
+    const int nf = h->h_status[0];
+    if (nf >= h->dec_B) {                                 // every utterance fired: the frames run = the longest utterance
+        std::vector<int> lens(h->dec_B);
+        CK(cudaMemcpyAsync(lens.data(), h->dparams.lens, (size_t)h->dec_B * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        int mx = 0; for (int v : lens) mx = std::max(mx, v);
+        h->dec_t = mx;
+    }
+    if (n_finished) *n_finished = nf;
+    if (t_done) *t_done = h->dec_t;
     return 0;
 }
 
@@ -622,11 +731,6 @@ extern "C" int tts_infer_host(TtsHandle* h, void* ws, const int64_t* phonemes, c
             if ((r = tts_decode_steps(h, ws, 16, stream))) return r;
             if ((r = tts_decode_status(h, ws, &td, &nf, stream))) return r;
             if (nf >= B) break;
-        }
-        if (nf >= B) {                                                      // first step at which all had fired
-            std::vector<int> lens(B);
-            CK(cudaMemcpy(lens.data(), wsp<int>(ws, L.lens), B * 4, cudaMemcpyDeviceToHost));
-            td = 0; for (int v : lens) td = std::max(td, v);
         }
     }
     // outputs staged in the (now free) sequence buffers, then copied to the host

@@ -64,7 +64,7 @@ int tts_load_weight(TtsHandle* h, const char* name, const float* host_data, int6
 int tts_finalize_weights(TtsHandle* h);
 
 /* ---- options ---------------------------------------------------------------------------------- */
-/* "decode_cluster": 1 (default) cluster-partitioned persistent decode kernel (16-CTA cluster per 8 utterances);
+/* "decode_cluster": 1 (default) cluster-partitioned persistent decode kernel (8-CTA cluster per "cluster_group" <= 8 utterances);
  *   0 grid-barrier persistent kernel.  "decode_persistent": 1 (default); 0 = one launch per phase (bring-up aid).
  * "decode_timestamps": 1 record per-phase timestamps (see tts_debug_phase_timestamps). */
 int tts_set_option(TtsHandle* h, const char* key, int64_t value);

@@ -42,3 +42,12 @@ for lo, hi in ((1, 50), (T // 2 - 25, T // 2 + 25), (T - 50, T)):
 print("mean us/step", out["us_per_step_mean"], " roofline us/step", decode_bytes(B, T, S) / T / 6468.6e3)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/phase_times.json", "w"), indent=1)
+m.set_option("print_info", 1)
+if os.environ.get("TTS_GROUPS"):
+    import time
+    for G in [int(x) for x in os.environ["TTS_GROUPS"].split(",")]:
+        m.set_option("cluster_group", G); m.set_option("decode_timestamps", 0)
+        m.profile_events = True; m.decode_ms.clear()
+        for _ in range(3):
+            m.inference(ph, pl, max_len=T, seed=7)
+        print(f"cluster_group={G}: decode {min(m.decode_ms):.2f} ms -> {1e3*min(m.decode_ms)/T:.1f} us/step")

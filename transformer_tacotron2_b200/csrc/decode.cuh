@@ -57,7 +57,7 @@ struct DecodeParams {
     int* lens; int* finished; int* n_finished; int* t_done;
     float* part_acc; float* part_ml; unsigned* part_cnt;
     unsigned* barrier;
-    unsigned long long* ts;        // optional [steps][n_phases] globaltimer stamps (debug / profiling)
+    unsigned long long* ts;        // optional [steps][64] globaltimer stamps (debug / profiling)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -405,7 +405,7 @@ decode_kernel(const DecodeParams p, int t0, int n_steps, int ph_begin, int ph_en
                 if (p.ts && blockIdx.x == 0 && threadIdx.x == 0) {
                     unsigned long long now;
                     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-                    p.ts[(size_t)step * p.n_phases + ph] = now;
+                    p.ts[(size_t)step * 64 + ph] = now;
                 }
             }
         }

@@ -29,7 +29,8 @@ struct TtsHandle {
     std::map<std::string, std::vector<float>> staged;
     bool finalized = false;
     int decode_persistent = 1, decode_timestamps = 0;
-    int decode_cluster = 1;                                           // 1: cluster-partitioned kernel when the device can co-schedule 16-CTA clusters
+    int cluster_group = 0;                                            // utterances per cluster (1..8); 0 = auto
+    int decode_cluster = 1;                                           // 1: cluster-partitioned kernel (8-CTA clusters)
     int cluster_ok = -1, max_clusters = 0;                            // probed lazily
     unsigned char* cl_wpack = nullptr;                                // [16][CLW_RANK_BYTES] (own allocation)
     ClusterParams cparams;
@@ -96,7 +97,7 @@ struct Ws {
         w.phases = take(64 * sizeof(PhaseDesc));
         w.d_xres = take(Bp * 512 * 4); w.d_y = take(Bp * 512 * 4); w.d_q = take(Bp * 512 * 4);
         w.d_a = take(Bp * 512 * 2); w.d_h = take(Bp * 2048 * 2); w.d_h1 = take(Bp * 256 * 2); w.d_h2 = take(Bp * 256 * 2);
-        w.ts = take((size_t)T * 64 * 8);
+        w.ts = take((size_t)(T + 1) * 64 * 8);
         w.x = take(M * 512 * 2); w.x2 = take(M * 512 * 2); w.wide = take(M * 2048 * 2); w.a = take(M * 512 * 2);
         w.y = take(M * 512 * 4); w.mel16 = take(M * 96 * 2); w.mel32 = take(M * 80 * 4);
         w.ph = take((size_t)B * S * 8); w.plens = take(B * 4); w.mlens = take(B * 4);
@@ -146,6 +147,8 @@ extern "C" int tts_set_option(TtsHandle* h, const char* key, int64_t value) {
     if (!strcmp(key, "decode_persistent")) { h->decode_persistent = value ? 1 : 0; return 0; }
     if (!strcmp(key, "decode_timestamps")) { h->decode_timestamps = value ? 1 : 0; return 0; }
     if (!strcmp(key, "decode_cluster")) { h->decode_cluster = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "cluster_group")) { if (value < 0 || value > CL_G) FAIL(TTS_E_ARG, "cluster_group must be 0 (auto) or 1..8"); h->cluster_group = (int)value; return 0; }
+    if (!strcmp(key, "print_info")) { fprintf(stderr, "[tts_b200] sms=%d cluster_ok=%d max_clusters=%d\n", h->num_sms, h->cluster_ok, h->max_clusters); return 0; }
     FAIL(TTS_E_ARG, std::string("unknown option ") + key);
 }
 
@@ -200,28 +203,37 @@ size_t pack_f32(Arena& ar, const float* v, size_t n, size_t npad = 0) {
 }
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// One segment of a cluster rank's weight stream: `ntiles` tiles of 16 output rows (global row indices in
-// rows[], -1 = zero row) x KP k-pairs starting at k-pair kp_lo, blocks in [tile][kp] order; each
-// 16 x 32 block = 2 x (32 lanes x uint4) in mma.sync m16n8k16 A-fragment order (decode_cluster.cuh).
-void pack_cluster_segment(std::vector<unsigned char>& out, const float* w, int N, int K, const std::vector<int>& rows, int kp_lo, int KP) {
-    const int ntiles = (int)rows.size() / 16;
-    const size_t base = out.size();
-    out.resize(base + (size_t)ntiles * KP * 1024, 0);
+// One segment of a cluster rank's weight stream (decode_cluster.cuh: cl_gemm).  rows[] lists the global output
+// row of every local column (NT tiles x 16; -1 = zero row).  Blocks are 16(n) x 32(k) in mma.sync m16n8k16
+// A-fragment order (2 x 32 lanes x uint4), ordered [chunk][warp][2] exactly as the consumer warps read them:
+//   typeB == false: warp w owns tile w % NT and K-slice kq = w / NT; chunk c holds its k-pairs kq*2*nchunks + 2c + {0,1}
+//   typeB == true : warp w owns tiles 2w, 2w+1; chunk c holds k-pair c of both (NT == 32)
+// kp_base offsets the k-pairs into W's K dimension (FFN2 K-slices).
+void pack_cluster_segment(std::vector<unsigned char>& out, const float* w, int N, int K, const std::vector<int>& rows,
+                          int kp_base, int KPT, int KSPLIT, bool typeB) {
+    const int NT = (int)rows.size() / 16;
+    const int nwarps = typeB ? 16 : NT * KSPLIT;
+    const int nchunks = typeB ? KPT : KPT / KSPLIT / 2;
     auto at = [&](int row, int k) -> uint32_t { return (row >= 0 && row < N && k < K) ? f2bf(w[(size_t)row * K + k]) : 0; };
-    for (int ti = 0; ti < ntiles; ++ti)
-        for (int kp = 0; kp < KP; ++kp) {
-            uint32_t* blk = reinterpret_cast<uint32_t*>(out.data() + base + ((size_t)ti * KP + kp) * 1024);
-            for (int ks = 0; ks < 2; ++ks)
-                for (int lane = 0; lane < 32; ++lane) {
-                    const int g = lane >> 2, t4 = lane & 3, k0 = (kp_lo + kp) * 32 + ks * 16 + t4 * 2;
-                    const int r0 = rows[ti * 16 + g], r1 = rows[ti * 16 + g + 8];
-                    uint32_t* q = blk + (ks * 32 + lane) * 4;
-                    q[0] = at(r0, k0) | (at(r0, k0 + 1) << 16);
-                    q[1] = at(r1, k0) | (at(r1, k0 + 1) << 16);
-                    q[2] = at(r0, k0 + 8) | (at(r0, k0 + 9) << 16);
-                    q[3] = at(r1, k0 + 8) | (at(r1, k0 + 9) << 16);
-                }
-        }
+    for (int c = 0; c < nchunks; ++c)
+        for (int wi = 0; wi < nwarps; ++wi)
+            for (int j = 0; j < 2; ++j) {
+                const int tile = typeB ? 2 * wi + j : wi % NT;
+                const int kp = kp_base + (typeB ? c : (wi / NT) * 2 * nchunks + 2 * c + j);
+                const size_t base = out.size();
+                out.resize(base + 1024, 0);
+                uint32_t* blk = reinterpret_cast<uint32_t*>(out.data() + base);
+                for (int ks = 0; ks < 2; ++ks)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = lane >> 2, t4 = lane & 3, k0 = kp * 32 + ks * 16 + t4 * 2;
+                        const int r0 = rows[tile * 16 + g], r1 = rows[tile * 16 + g + 8];
+                        uint32_t* q = blk + (ks * 32 + lane) * 4;
+                        q[0] = at(r0, k0) | (at(r0, k0 + 1) << 16);
+                        q[1] = at(r1, k0) | (at(r1, k0 + 1) << 16);
+                        q[2] = at(r0, k0 + 8) | (at(r0, k0 + 9) << 16);
+                        q[3] = at(r1, k0 + 8) | (at(r1, k0 + 9) << 16);
+                    }
+            }
 }
 std::vector<int> iota_rows(int lo, int n) { std::vector<int> r(n); for (int i = 0; i < n; ++i) r[i] = lo + i; return r; }
 }  // namespace
@@ -364,27 +376,27 @@ extern "C" int tts_finalize_weights(TtsHandle* h) {
         for (int rk = 0; rk < CL_SIZE; ++rk) {
             std::vector<unsigned char> seg;
             seg.reserve(CLW_RANK_BYTES);
-            pack_cluster_segment(seg, wf1, 256, 80, iota_rows(16 * rk, 16), 0, 3);
-            pack_cluster_segment(seg, wf2, 256, 256, iota_rows(16 * rk, 16), 0, 8);
-            pack_cluster_segment(seg, wpj, 512, 256, iota_rows(32 * rk, 32), 0, 8);
+            pack_cluster_segment(seg, wf1, 256, 80, iota_rows(32 * rk, 32), 0, 4, 2, false);      // K 80 -> 128 (zeros)
+            pack_cluster_segment(seg, wf2, 256, 256, iota_rows(32 * rk, 32), 0, 8, 4, false);
+            pack_cluster_segment(seg, wpj, 512, 256, iota_rows(64 * rk, 64), 0, 8, 4, false);
             for (int l = 0; l < 6; ++l) {
                 const std::string p = "decoder.layers." + std::to_string(l);
                 if ((r = cat3(p + ".self_attn", w3, b3))) return r;
                 GET(wo, p + ".self_attn.wo.weight", (size_t)D * D); GET(wq2, p + ".cross_attn.wq.weight", (size_t)D * D);
                 GET(wo2, p + ".cross_attn.wo.weight", (size_t)D * D);
                 GET(w1, p + ".ffn.w1.weight", (size_t)F * D); GET(w2, p + ".ffn.w2.weight", (size_t)D * F);
-                std::vector<int> qrows(96);                       // 32 dims of q, k, v of head rk/2, half rk%2
-                for (int cc = 0; cc < 96; ++cc) qrows[cc] = (cc >> 5) * 512 + (rk >> 1) * 64 + (rk & 1) * 32 + (cc & 31);
-                pack_cluster_segment(seg, w3.data(), 3 * D, D, qrows, 0, 16);
-                pack_cluster_segment(seg, wo, D, D, iota_rows(32 * rk, 32), 0, 16);
-                pack_cluster_segment(seg, wq2, D, D, iota_rows(32 * rk, 32), 0, 16);
-                pack_cluster_segment(seg, wo2, D, D, iota_rows(32 * rk, 32), 0, 16);
-                pack_cluster_segment(seg, w1, F, D, iota_rows(128 * rk, 128), 0, 16);
-                pack_cluster_segment(seg, w2, D, F, iota_rows(0, 512), 4 * rk, 4);      // K-slice [128 rk, 128 rk + 128)
+                std::vector<int> qrows(192);                      // q, k, v (64 dims each) of head rk
+                for (int cc = 0; cc < 192; ++cc) qrows[cc] = (cc >> 6) * 512 + rk * 64 + (cc & 63);
+                pack_cluster_segment(seg, w3.data(), 3 * D, D, qrows, 0, 16, 1, false);
+                pack_cluster_segment(seg, wo, D, D, iota_rows(64 * rk, 64), 0, 16, 4, false);
+                pack_cluster_segment(seg, wq2, D, D, iota_rows(64 * rk, 64), 0, 16, 4, false);
+                pack_cluster_segment(seg, wo2, D, D, iota_rows(64 * rk, 64), 0, 16, 4, false);
+                pack_cluster_segment(seg, w1, F, D, iota_rows(256 * rk, 256), 0, 16, 1, false);
+                pack_cluster_segment(seg, w2, D, F, iota_rows(0, 512), 8 * rk, 8, 1, true);        // K-slice [256 rk, 256 rk + 256)
             }
             std::vector<int> hrows(16);
             for (int i = 0; i < 16; ++i) hrows[i] = (rk < 6 && 16 * rk + i < 81) ? 16 * rk + i : -1;
-            pack_cluster_segment(seg, whead.data(), 81, D, hrows, 0, 16);
+            pack_cluster_segment(seg, whead.data(), 81, D, hrows, 0, 16, 8, false);
             if (seg.size() != CLW_RANK_BYTES) FAIL(TTS_E_STATE, "cluster weight stream size mismatch");
             memcpy(clw.data() + (size_t)rk * CLW_RANK_BYTES, seg.data(), CLW_RANK_BYTES);
         }
@@ -601,7 +613,7 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
     p.part_acc = wsp<float>(ws, L.part_acc); p.part_ml = wsp<float>(ws, L.part_ml); p.part_cnt = wsp<unsigned>(ws, L.part_cnt);
 
     ClusterParams& cp = h->cparams; memset(&cp, 0, sizeof(cp));
-    cp.B = B; cp.Tmax = max_len; cp.S = S; cp.ngroups = (B + CL_G - 1) / CL_G;
+    cp.B = B; cp.Tmax = max_len; cp.S = S;
     cp.seed = seed; cp.utt_offset = utt_offset; cp.dec_alpha = h->dec_alpha; cp.pe = h->pe;
     cp.wpack = h->cl_wpack; cp.b_fc1 = h->pre_b1; cp.b_fc2 = h->pre_b2; cp.b_proj = h->pre_bp; cp.b_head = h->head_b;
     for (int l = 0; l < 6; ++l) {
@@ -610,10 +622,9 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
     }
     cp.self_kv = skv; cp.cross_kv = ckv; cp.plens = plens;
     cp.mel_before = p.mel_before; cp.stop_logits = p.stop_logits; cp.lens = p.lens; cp.finished = p.finished; cp.n_finished = p.n_finished;
-    if (h->cluster_ok < 0) {                                            // can this device co-schedule 16-CTA clusters of this kernel?
+    if (h->cluster_ok < 0) {                                            // how many 8-CTA clusters of this kernel can be co-resident?
         h->cluster_ok = 0;
-        if (cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-            cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES) == cudaSuccess) {
+        if (cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES) == cudaSuccess) {
             cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
             cfg.gridDim = dim3(CL_SIZE * 8); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES;
             cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
@@ -624,6 +635,10 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
         }
         cudaGetLastError();
     }
+    // utterances per cluster: as few as the co-resident cluster count allows (more SMs stream K/V), at most 8
+    cp.G = h->cluster_group > 0 ? std::min(CL_G, h->cluster_group)
+                                : std::min(CL_G, std::max(1, (B + std::max(1, h->max_clusters) - 1) / std::max(1, h->max_clusters)));
+    cp.ngroups = (B + cp.G - 1) / cp.G;
     return 0;
 }
 
@@ -643,10 +658,11 @@ extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* strea
         cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
+        h->cparams.ts = h->decode_timestamps ? wsp<unsigned long long>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).ts) : nullptr;
         CK(cudaLaunchKernelEx(&cfg, decode_cluster_kernel, h->cparams, h->dec_t, n_steps));
         ++launch_counter();
     } else if (h->decode_persistent) {
-        p.ts = h->decode_timestamps ? wsp<unsigned long long>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).ts) + (size_t)h->dec_t * p.n_phases : nullptr;
+        p.ts = h->decode_timestamps ? wsp<unsigned long long>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).ts) + (size_t)h->dec_t * 64 : nullptr;
         CK(cudaMemsetAsync(p.barrier, 0, 4, st));
         int t0 = h->dec_t, ns = n_steps, pb = 0, pe = p.n_phases, pers = 1;
         void* args[] = {&p, &t0, &ns, &pb, &pe, &pers};
@@ -826,9 +842,9 @@ extern "C" int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, cons
 // profiling aid: copy the per-phase globaltimer stamps of the persistent decode kernel to the host.
 extern "C" int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long long* out, int n_steps, void* stream) {
     if (!h || !ws || !out || n_steps <= 0) return TTS_E_ARG;
-    if (!h->dec_active || n_steps > h->dec_T) FAIL(TTS_E_STATE, "no decode session / too many steps");
+    if (!h->dec_active || n_steps != h->dec_T) FAIL(TTS_E_STATE, "no decode session / n_steps must equal max_len");
     const Ws L = Ws::make(h->dec_B, h->dec_S, h->dec_T);
-    CK(cudaMemcpyAsync(out, wsp<unsigned long long>(ws, L.ts), (size_t)n_steps * h->dparams.n_phases * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaMemcpyAsync(out, wsp<unsigned long long>(ws, L.ts), (size_t)(n_steps + 1) * 64 * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return h->dparams.n_phases;
 }

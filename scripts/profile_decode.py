@@ -39,6 +39,12 @@ for lo, hi in ((1, 50), (T // 2 - 25, T // 2 + 25), (T - 50, T)):
     print(f"steps {lo}-{hi}: {w.sum(1).mean():.1f} us/step")
     for k in row:
         print(f"   {k:11s} {row[k]:7.2f} us/phase x{len(groups[k]):2d} = {tot[k]:7.1f} us/step")
+a = m.all_stamps.double()
+if (a[:, 52] > 0).any():
+    w = a[T // 2 - 100: T // 2 + 100]
+    print("O-proj L0 breakdown (us): gemm->52 %.2f | push %.2f | cl_sync %.2f | LN %.2f" % (
+        float((w[:, 52] - w[:, 4]).mean() / 1e3), float((w[:, 53] - w[:, 52]).mean() / 1e3),
+        float((w[:, 54] - w[:, 53]).mean() / 1e3), float((w[:, 5] - w[:, 54]).mean() / 1e3)))
 print("mean us/step", out["us_per_step_mean"], " roofline us/step", decode_bytes(B, T, S) / T / 6468.6e3)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/phase_times.json", "w"), indent=1)
@@ -51,3 +57,13 @@ if os.environ.get("TTS_GROUPS"):
         for _ in range(3):
             m.inference(ph, pl, max_len=T, seed=7)
         print(f"cluster_group={G}: decode {min(m.decode_ms):.2f} ms -> {1e3*min(m.decode_ms)/T:.1f} us/step")
+
+if os.environ.get("TTS_DBG_MODES"):
+    m.set_option("cluster_group", 0); m.set_option("decode_timestamps", 0)
+    for mode in [int(x) for x in os.environ["TTS_DBG_MODES"].split(",")]:
+        m.set_option("debug_mode", mode)
+        m.profile_events = True; m.decode_ms.clear()
+        for _ in range(2):
+            m.inference(ph, pl, max_len=T, seed=7)
+        print(f"debug_mode={mode}: decode {min(m.decode_ms):.2f} ms -> {1e3*min(m.decode_ms)/T:.1f} us/step")
+    m.set_option("debug_mode", 0)

@@ -4,14 +4,11 @@ import os
 import torch
 
 
-def make_b200_model(oracle_model, persistent=True, cluster=True):
+def make_b200_model(oracle_model, cluster_group=0):
     from transformer_tacotron2_b200 import TransformerTTS
     m = TransformerTTS()
     m.load_state_dict(oracle_model.state_dict())
-    if os.environ.get("TTS_FORCE_PER_PHASE") == "1":       # bring-up aid: never launch the persistent kernel
-        persistent = False
-    m.set_option("decode_persistent", 1 if persistent else 0)
-    m.set_option("decode_cluster", 1 if cluster else 0)
+    m.set_option("cluster_group", cluster_group)           # 0 = auto; 1..8 utterances per 8-CTA cluster
     return m
 
 

@@ -17,14 +17,20 @@
 //     in flight per SM (profiles/r01_bulk_bw_ubench.md: what one SM needs to pull > 100 GB/s).
 // Weights are packed per CTA rank in exactly the order the step consumes them (tts_b200.cu), each
 // 16(n) x 32(k) block in A-fragment order, blocks ordered [chunk][warp][2].
+// KV-cache layout (P18, adapted to the tensor-core decode attention): per (layer, b, h) and padded length
+// Lp = roundup(L, 16):  K row-major [Lp][64];  V in 16-row blocks stored transposed [Lp/16][64 d][16 rows],
+// so that a 16-row chunk of either is one contiguous 2 KB bulk copy and both are A operands of
+// mma.sync.m16n8k16 straight from shared memory with conflict-free 16-/8-byte loads (the k index of an
+// MMA may be permuted freely as long as A and B agree).
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 #include "philox.cuh"
 
 namespace tts {
 
 constexpr int CL_SIZE = 8, CL_CONSUMERS = 512, CL_THREADS = 544, CL_WARPS = 16, CL_G = 8;
-constexpr int CL_STAGES = 4, CL_STAGE_BYTES = 32768, CL_KV_ROWS = 128;
+constexpr int CL_STAGES = 4, CL_STAGE_BYTES = 32768, CL_KV_ROWS = 16;   // K/V chunk: 16 rows of every pair of the CTA
 constexpr int CL_NS = 512 / CL_SIZE;                 // 64: columns of a 512-wide output owned by one rank
 
 // bytes of one rank's packed weight segments (stream order: fc1 fc2 proj | 6 x (qkv o q2 o2 w1 w2) | head)
@@ -55,16 +61,22 @@ struct ClusterLayerParams {
     const float *bqkv, *bo, *bq2, *bo2, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b, *ln3g, *ln3b;
 };
 struct ClusterParams {
+    // TMA descriptors of the two K/V caches viewed as 4-D bf16 tensors [12*B (layer,kv,b)][8 h][Lpad rows][64]:
+    // one box {64, 16, 1, G} = the 16-row chunk of all G utterances of a cluster for one head, in one copy
+    alignas(64) CUtensorMap tm_self;
+    alignas(64) CUtensorMap tm_cross;
     int B, Tmax, S, G, ngroups;                  // G utterances per cluster (<= 8)
+    int Tpad, Spad;                              // cache row capacities, multiples of 16
     uint64_t seed; int utt_offset; float dec_alpha; const float* pe;
     const unsigned char* wpack;                  // [8][CLW_RANK_BYTES]
     const float *b_fc1, *b_fc2, *b_proj, *b_head;
     ClusterLayerParams layer[6];
-    bf16* self_kv;                               // [6][2][B][8][Tmax][64]
-    const bf16* cross_kv;                        // [6][2][B][8][S][64]
+    bf16* self_kv;                               // [6][2][B][8][Tpad*64]  (K row-major, V blocked-transposed)
+    const bf16* cross_kv;                        // [6][2][B][8][Spad*64]
     const int* plens;
     float* mel_before; float* stop_logits; int* lens; int* finished; int* n_finished;
     unsigned long long* ts;                      // optional [Tmax][64] %globaltimer stamps (cluster 0, rank 0)
+    int dbg;                                     // profiling experiments (results invalid): 1 skip attention math, 2 contiguous K/V copies
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -106,6 +118,10 @@ TTS_D bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 TTS_D void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
+TTS_D void tma_g2s_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 TTS_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
@@ -119,17 +135,22 @@ struct ClCtx {
     int b0, G;                           // group base utterance, rows in this group
     uint32_t consumed;                   // chunks consumed (uniform over the consumer warps)
     uint32_t sync_phase;                 // cluster barrier phase counter
+    int dbg;
 };
 
 // The ordered stream of chunks of one step for one rank.  seg: 0 fc1, 1 fc2, 2 proj,
 // 3+8l+{0 qkv, 1 self-KV, 2 o, 3 q2, 4 cross-KV, 5 o2, 6 w1, 7 w2}, 51 head.
-TTS_D int seg_chunks(int seg, int t, int S, int G, int rank) {
+TTS_D int seg_chunks(int seg, int t, int S, int G, int rank, int dbg = 0) {
+    if (dbg == 6 || dbg == 7) {                          // profiling experiments: weights only / K,V only
+        const bool kv = seg >= 3 && seg < 51 && (((seg - 3) & 7) == 1 || ((seg - 3) & 7) == 4);
+        if ((dbg == 6 && kv) || (dbg == 7 && !kv)) return 0;
+    }
     if (seg < 3) return 1;
     if (seg == 51) return rank < 6 ? 1 : 0;
     switch ((seg - 3) & 7) {
     case 0: case 6: case 7: return 8;
-    case 1: return G * ((t + CL_KV_ROWS - 1) / CL_KV_ROWS);
-    case 4: return G * ((S + CL_KV_ROWS - 1) / CL_KV_ROWS);
+    case 1: return (t + CL_KV_ROWS - 1) / CL_KV_ROWS;
+    case 4: return (S + CL_KV_ROWS - 1) / CL_KV_ROWS;
     default: return 2;
     }
 }
@@ -141,10 +162,13 @@ TTS_D uint32_t seg_weight_bytes(int seg) {          // bytes per chunk of a weig
     return CL_STAGE_BYTES;
 }
 
-// Producer warp (lane 0): issue the whole chunk stream of steps [t0, t_end) in order, each chunk as soon as
-// its ring slot has been released by all 16 consumer warps.  Stops early when the consumers raise `stop`.
+// Producer warp: issue the whole chunk stream of steps [t0, t_end) in order, each chunk as soon as its ring
+// slot has been released by all 16 consumer warps.  Weight chunks are one bulk copy; a K/V chunk is two TMA
+// tensor copies (the 16-row K box and the V block box of all G pairs): separate <= 2 KB bulk copies cost ~50 ns
+// each in the copy engine (profiles/r01_bulk_bw_ubench.md) and capped the stream at ~40 GB/s per SM.  Stops early when the
+// consumers raise flags[1].  The control flow is warp-uniform.
 TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* full, uint64_t* empty, volatile int* flags,
-                       int rank, int b0, int G, int t0, int t_end) {
+                       int rank, int b0, int G, int t0, int t_end, int lane) {
     const uint64_t pol_w = l2_policy_evict_last(), pol_kv = l2_policy_evict_first();
     uint32_t issued = 0;
     const unsigned char* wbase = p.wpack + (size_t)rank * CLW_RANK_BYTES;
@@ -152,52 +176,60 @@ TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* fu
     for (int t = t0; t < t_end && !stopped; ++t) {
         size_t woff = 0;
         for (int seg = 0; seg <= 51 && !stopped; ++seg) {
-            const int n = seg_chunks(seg, t, p.S, G, rank);
+            const int n = seg_chunks(seg, t, p.S, G, rank, p.dbg);
             const int sub = (seg < 3 || seg == 51) ? -1 : ((seg - 3) & 7);
             for (int i = 0; i < n; ++i) {
                 const int stage = issued % CL_STAGES;
                 const uint32_t use = issued / CL_STAGES;
                 if (use > 0) {
-                    while (!mbar_try_wait(&empty[stage], (use & 1) ^ 1)) {
-                        if (flags[1]) { stopped = true; break; }
+                    for (;;) {                           // all lanes poll (see cl_acquire); the decision is made warp-uniform
+                        const int ok = mbar_try_wait(&empty[stage], (use & 1) ^ 1) ? 1 : 0;
+                        if (__any_sync(0xffffffffu, ok)) break;
+                        if (__any_sync(0xffffffffu, flags[1])) { stopped = true; break; }
                     }
                     if (stopped) break;
                 }
                 unsigned char* dst = smem + SM_RING + stage * CL_STAGE_BYTES;
-                if (sub == 1 || sub == 4) {                      // K rows + V rows of one (utterance, head) pair
-                    const int l = (seg - 3) >> 3;
-                    const int L = sub == 1 ? t : p.S, Lmax = sub == 1 ? p.Tmax : p.S;
-                    const int nck = (L + CL_KV_ROWS - 1) / CL_KV_ROWS;
-                    const int pr = i / nck, ci = i - pr * nck;
-                    const int b = b0 + pr;
-                    const int row0 = ci * CL_KV_ROWS, nrows = min(CL_KV_ROWS, L - row0);
-                    const bf16* base = sub == 1 ? p.self_kv : p.cross_kv;
-                    const size_t kidx = ((((size_t)(l * 2) * p.B + b) * kHeads + rank) * Lmax + row0) * kDHead;
-                    const size_t vidx = ((((size_t)(l * 2 + 1) * p.B + b) * kHeads + rank) * Lmax + row0) * kDHead;
-                    const uint32_t bytes = (uint32_t)nrows * 128u;
-                    asm volatile("fence.proxy.async;" ::: "memory");   // rows written with st.global earlier in this launch
-                    mbar_expect_tx(&full[stage], 2 * bytes);
-                    bulk_g2s(dst, base + kidx, bytes, &full[stage], pol_kv);
-                    bulk_g2s(dst + CL_KV_ROWS * 128, base + vidx, bytes, &full[stage], pol_kv);
-                } else {
+                if (sub == 1 || sub == 4) {                      // 16 K rows + one V block of every pair (b0.., head rank): 2 TMA boxes
+                    if (lane == 0) {
+                        const int l = (seg - 3) >> 3;
+                        const CUtensorMap* tm = sub == 1 ? &p.tm_self : &p.tm_cross;
+                        mbar_expect_tx(&full[stage], 2u * (uint32_t)p.G * 2048u);
+                        if (p.dbg == 2) {
+                            const bf16* base = sub == 1 ? p.self_kv : p.cross_kv;
+                            const int Lp = sub == 1 ? p.Tpad : p.Spad;
+                            const size_t idx = ((((size_t)(l * 2) * p.B + b0) * kHeads + rank) * Lp + (size_t)(i % 8) * p.G * CL_KV_ROWS) * kDHead;
+                            bulk_g2s(dst, base + idx, (uint32_t)p.G * 2048u, &full[stage], pol_kv);
+                            bulk_g2s(dst + 16384, base + idx + (size_t)p.B * kHeads * Lp * kDHead, (uint32_t)p.G * 2048u, &full[stage], pol_kv);
+                        } else {
+                        tma_g2s_4d(dst, tm, 0, i * CL_KV_ROWS, rank, (l * 2) * p.B + b0, &full[stage], pol_kv);
+                        tma_g2s_4d(dst + 16384, tm, 0, i * CL_KV_ROWS, rank, (l * 2 + 1) * p.B + b0, &full[stage], pol_kv);
+                        }
+                    }
+                } else if (lane == 0) {
                     const uint32_t bytes = seg_weight_bytes(seg);
                     mbar_expect_tx(&full[stage], bytes);
                     bulk_g2s(dst, wbase + woff, bytes, &full[stage], pol_w);
-                    woff += bytes;
                 }
+                if (!(sub == 1 || sub == 4)) woff += seg_weight_bytes(seg);
                 ++issued;
             }
         }
     }
     // wait until the consumers are done with the group, then drain copies that were issued but never consumed
-    while (!flags[1]) {}
-    __threadfence_block();
-    const uint32_t final_consumed = (uint32_t)flags[2];
-    for (uint32_t i = final_consumed; i < issued; ++i) mbar_wait(&full[i % CL_STAGES], (i / CL_STAGES) & 1);
+    if (lane == 0) {
+        while (!flags[1]) {}
+        __threadfence_block();
+        const uint32_t final_consumed = (uint32_t)flags[2];
+        for (uint32_t i = final_consumed; i < issued; ++i) mbar_wait(&full[i % CL_STAGES], (i / CL_STAGES) & 1);
+    }
+    __syncwarp();
 }
 
 TTS_D unsigned char* cl_acquire(ClCtx& c) {
     const int stage = c.consumed % CL_STAGES;
+    // every lane polls: a single polling lane with the rest parked at __syncwarp wakes up ~2x slower
+    // (scripts/ubench/pipe_rtt.cu: 0.57 -> 0.32 us per 32 KB chunk)
     mbar_wait(&c.full[stage], (c.consumed / CL_STAGES) & 1);
     return c.smem + SM_RING + stage * CL_STAGE_BYTES;
 }
@@ -209,6 +241,7 @@ TTS_D void cl_release(ClCtx& c) {
 // cluster-wide barrier of the consumer warps: my DSMEM pushes are visible to every peer afterwards
 TTS_D void cl_sync(ClCtx& c) {
     consumer_bar();
+    if (c.dbg == 3) return;                              // profiling experiment: no cluster barrier (results invalid)
     if (c.tid < CL_SIZE) mbar_arrive_remote(map_to_rank(smem_u32(c.csync), (uint32_t)c.tid));
     while (!mbar_try_wait_cluster(c.csync, c.sync_phase & 1)) {}
     ++c.sync_phase;
@@ -219,11 +252,28 @@ TTS_D void cl_sync(ClCtx& c) {
 // (w % NT) and K-slice (w / NT) and consumes blocks 2w, 2w+1 of every chunk (k-pairs kq*2*nchunks + 2c + j);
 // typeB (FFN2): warp w owns tiles 2w, 2w+1 and chunk c carries k-pair c of both.  Accumulators stay in
 // registers across chunks; K-split partials are reduced once per segment through shared memory.
-template <class Epi>
-TTS_D void cl_gemm(ClCtx& c, int nchunks, int NT, int KSPLIT, bool typeB, const bf16* X, int ldx, Epi epi) {
+template <class BiasFn, class Epi>
+TTS_D void cl_gemm(ClCtx& c, int nchunks, int NT, int KSPLIT, bool typeB, const bf16* X, int ldx, BiasFn biasf, Epi epi) {
     const int nactive = typeB ? CL_WARPS : NT * KSPLIT;
     const bool active = c.warp < nactive;
     const int kq = typeB ? 0 : c.warp / NT;
+    const int g = c.lane >> 2, t4 = c.lane & 3;
+    const bool direct = typeB || KSPLIT == 1;            // complete sums end up in registers
+    // biases (global memory) are fetched before the first chunk arrives, off the critical path
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+    if (direct) {
+        if (active) {
+            const int tile0 = typeB ? c.warp * 2 : c.warp;
+            bias[0] = biasf(tile0, g); bias[1] = biasf(tile0, g + 8);
+            if (typeB) { bias[2] = biasf(tile0 + 1, g); bias[3] = biasf(tile0 + 1, g + 8); }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int o = c.tid + k * CL_CONSUMERS;
+            if (o < NT * 128) bias[k] = biasf(o >> 7, (o >> 3) & 15);
+        }
+    }
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
     for (int ch = 0; ch < nchunks; ++ch) {
         const unsigned char* st = cl_acquire(c);
@@ -243,16 +293,15 @@ TTS_D void cl_gemm(ClCtx& c, int nchunks, int NT, int KSPLIT, bool typeB, const 
         }
         cl_release(c);
     }
-    const int g = c.lane >> 2, t4 = c.lane & 3;
-    if (typeB || KSPLIT == 1) {                          // complete sums are in registers
+    if (direct) {
         if (active) {
             const int tile0 = typeB ? c.warp * 2 : c.warp;
             const int m0 = t4 * 2;
-            if (m0 < c.G) { epi(tile0, g, m0, acc0[0]); epi(tile0, g + 8, m0, acc0[2]); }
-            if (m0 + 1 < c.G) { epi(tile0, g, m0 + 1, acc0[1]); epi(tile0, g + 8, m0 + 1, acc0[3]); }
+            if (m0 < c.G) { epi(tile0, g, m0, acc0[0] + bias[0]); epi(tile0, g + 8, m0, acc0[2] + bias[1]); }
+            if (m0 + 1 < c.G) { epi(tile0, g, m0 + 1, acc0[1] + bias[0]); epi(tile0, g + 8, m0 + 1, acc0[3] + bias[1]); }
             if (typeB) {
-                if (m0 < c.G) { epi(tile0 + 1, g, m0, acc1[0]); epi(tile0 + 1, g + 8, m0, acc1[2]); }
-                if (m0 + 1 < c.G) { epi(tile0 + 1, g, m0 + 1, acc1[1]); epi(tile0 + 1, g + 8, m0 + 1, acc1[3]); }
+                if (m0 < c.G) { epi(tile0 + 1, g, m0, acc1[0] + bias[2]); epi(tile0 + 1, g + 8, m0, acc1[2] + bias[3]); }
+                if (m0 + 1 < c.G) { epi(tile0 + 1, g, m0 + 1, acc1[1] + bias[2]); epi(tile0 + 1, g + 8, m0 + 1, acc1[3] + bias[3]); }
             }
         }
         consumer_bar();
@@ -264,11 +313,15 @@ TTS_D void cl_gemm(ClCtx& c, int nchunks, int NT, int KSPLIT, bool typeB, const 
             *reinterpret_cast<float2*>(r + (g + 8) * 8 + t4 * 2) = make_float2(acc0[2], acc0[3]);
         }
         consumer_bar();
-        for (int o = c.tid; o < NT * 128; o += CL_CONSUMERS) {
-            const int ti = o >> 7, n = (o >> 3) & 15, m = o & 7;
-            float v = 0.f;
-            for (int q = 0; q < KSPLIT; ++q) v += red[(q * NT + ti) * 128 + n * 8 + m];     // fixed order: deterministic
-            if (m < c.G) epi(ti, n, m, v);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int o = c.tid + k * CL_CONSUMERS;
+            if (o < NT * 128) {
+                const int ti = o >> 7, n = (o >> 3) & 15, m = o & 7;
+                float v = bias[k];
+                for (int q = 0; q < KSPLIT; ++q) v += red[(q * NT + ti) * 128 + n * 8 + m];     // fixed order: deterministic
+                if (m < c.G) epi(ti, n, m, v);
+            }
         }
         consumer_bar();
     }
@@ -297,9 +350,20 @@ TTS_D void push_bf16_all(const ClCtx& c, const float* stage, int ld, bf16* dst, 
     }
 }
 
-// LayerNorm of the gathered rows: ybuf -> xres (f32) + xa (bf16); warp m < G owns row m.
-TTS_D void cl_layernorm(ClCtx& c, const float* g, const float* b) {
+// LayerNorm of the gathered rows: ybuf -> xres (f32) + xa (bf16); warp m < G owns row m.  The affine
+// parameters (global memory) are fetched by ln_prefetch() BEFORE the cluster barrier the rows are waited on.
+struct LnAffine { float4 g[4], b[4]; };
+TTS_D void ln_prefetch(const ClCtx& c, const float* g, const float* b, LnAffine& a) {
     if (c.warp < c.G) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a.g[i] = __ldg(reinterpret_cast<const float4*>(g + i * 128 + c.lane * 4));
+            a.b[i] = __ldg(reinterpret_cast<const float4*>(b + i * 128 + c.lane * 4));
+        }
+    }
+}
+TTS_D void cl_layernorm(ClCtx& c, const LnAffine& a) {
+    if (c.warp < c.G && c.dbg != 4) {
         const float* y = reinterpret_cast<const float*>(c.smem + SM_YBUF) + c.warp * 512;
         float* xr = reinterpret_cast<float*>(c.smem + SM_XRES) + c.warp * 512;
         bf16* xa = reinterpret_cast<bf16*>(c.smem + SM_XA) + c.warp * LDX512;
@@ -320,9 +384,8 @@ TTS_D void cl_layernorm(ClCtx& c, const float* g, const float* b) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int col = i * 128 + c.lane * 4;
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + col)), b4 = __ldg(reinterpret_cast<const float4*>(b + col));
-            const float o0 = (v[i * 4] - mean) * rstd * g4.x + b4.x, o1 = (v[i * 4 + 1] - mean) * rstd * g4.y + b4.y;
-            const float o2 = (v[i * 4 + 2] - mean) * rstd * g4.z + b4.z, o3 = (v[i * 4 + 3] - mean) * rstd * g4.w + b4.w;
+            const float o0 = (v[i * 4] - mean) * rstd * a.g[i].x + a.b[i].x, o1 = (v[i * 4 + 1] - mean) * rstd * a.g[i].y + a.b[i].y;
+            const float o2 = (v[i * 4 + 2] - mean) * rstd * a.g[i].z + a.b[i].z, o3 = (v[i * 4 + 3] - mean) * rstd * a.g[i].w + a.b[i].w;
             *reinterpret_cast<float4*>(xr + col) = make_float4(o0, o1, o2, o3);
             *reinterpret_cast<uint2*>(xa + col) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
         }
@@ -330,115 +393,133 @@ TTS_D void cl_layernorm(ClCtx& c, const float* g, const float* b) {
     consumer_bar();
 }
 
-// Attention of this CTA's pairs (all rows of the group, head = rank) over K/V chunks from the ring.
-// self: rows 0..t-1 from the cache + the newest row (k_t, v_t) from qkvbuf.  cross: rows 0..len-1.
+// Attention of this CTA's pairs (utterance w of the group, head = rank): warp w < G owns pair w and runs a
+// flash-style online softmax over 16-row chunks on the tensor cores:
+//   scores[16 rows] = K_chunk[16 x 64] . q        4 x mma.m16n8k16 (A = K rows, B = q in column 0)
+//   out[64 d]      += V_chunk^T[64 x 16] . p      4 x mma.m16n8k16 (A = V^T block, B = p in column 0)
+// self: rows 0..t-1 from the cache chunks + the newest row (k_t, v_t) from qkvbuf; cross: rows 0..len-1.
 // Output rows are staged in `stage` [8][64] and pushed to abuf[m][rank*64 ..] of every CTA.
 TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, float* stage) {
     const float* qkv = reinterpret_cast<const float*>(c.smem + SM_QKV);
-    float* am = reinterpret_cast<float*>(c.smem + SM_AMERGE);
-    const int g4 = c.lane >> 3, sub = c.lane & 7;
-    const float qscale = 0.125f * kLog2e;
+    float* pscr = reinterpret_cast<float*>(c.smem + SM_AMERGE) + c.warp * 68;      // 16 probabilities of the current chunk
+    const int g = c.lane >> 2, t4 = c.lane & 3;
+    const float qs = 0.125f * kLog2e;
     const int L = self ? t : p.S;
     const int nck = (L + CL_KV_ROWS - 1) / CL_KV_ROWS;
-    for (int gi = 0; gi < c.G; ++gi) {
-        const int vlen = self ? L : min(L, __ldg(p.plens + c.b0 + gi));
-        float q[8];
+    const int gi = c.warp >> 1, par2 = c.warp & 1;         // warps 2p, 2p+1 share pair p: even / odd chunks
+    const bool active = gi < c.G;
+    int vlen = L;
+    uint32_t qb0[4] = {0, 0, 0, 0}, qb1[4] = {0, 0, 0, 0};
+    if (active) {
+        if (!self) vlen = min(L, __ldg(p.plens + c.b0 + gi));
+        if (g == 0) {                                    // B fragments of q (column 0 only), k slots <-> dims 16 t4 + 4 ks + {0..3}
 #pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] = qkv[gi * 192 + sub * 8 + j] * qscale;
-        float m = -INFINITY, l = 0.f, acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int ci = 0; ci < nck; ++ci) {
-            const unsigned char* st = cl_acquire(c);
-            const int nrows = min(CL_KV_ROWS, vlen - ci * CL_KV_ROWS);
-            uint4 kk[2], vv[2];
-            float s[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int r = c.warp * 8 + u * 4 + g4;
-                if (r < nrows) {
-                    kk[u] = *reinterpret_cast<const uint4*>(st + r * 128 + sub * 16);
-                    vv[u] = *reinterpret_cast<const uint4*>(st + CL_KV_ROWS * 128 + r * 128 + sub * 16);
-                } else { kk[u] = make_uint4(0, 0, 0, 0); vv[u] = make_uint4(0, 0, 0, 0); }
+            for (int ks = 0; ks < 4; ++ks) {
+                const float* qp = qkv + gi * 192 + 16 * t4 + 4 * ks;
+                qb0[ks] = pack_bf16x2(qp[0] * qs, qp[1] * qs);
+                qb1[ks] = pack_bf16x2(qp[2] * qs, qp[3] * qs);
             }
-            cl_release(c);
+        }
+    }
+    float m = -INFINITY, l = 0.f, o[4][4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const float2 k0 = unpack_bf16x2(kk[u].x), k1 = unpack_bf16x2(kk[u].y), k2 = unpack_bf16x2(kk[u].z), k3 = unpack_bf16x2(kk[u].w);
-                float ps = q[0] * k0.x + q[1] * k0.y + q[2] * k1.x + q[3] * k1.y + q[4] * k2.x + q[5] * k2.y + q[6] * k3.x + q[7] * k3.y;
-                ps += __shfl_xor_sync(0xffffffffu, ps, 1);
-                ps += __shfl_xor_sync(0xffffffffu, ps, 2);
-                ps += __shfl_xor_sync(0xffffffffu, ps, 4);
-                s[u] = (c.warp * 8 + u * 4 + g4 < nrows) ? ps : -INFINITY;
+    for (int i = 0; i < 4; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    for (int ci = 0; ci < nck; ++ci) {
+        const unsigned char* st = cl_acquire(c);
+        uint32_t kr[8], kr8[8];
+        uint2 vf[4][2];
+        const bool mine = active && (ci & 1) == par2;
+        if (mine) {
+            const unsigned char* kb = st + gi * 2048;
+            const unsigned char* vb = st + 16384 + gi * 2048;
+            const int par = g & 1;                       // XOR-ordered 16-byte loads: conflict-free at a 128 B row stride
+            const uint4 ka = *reinterpret_cast<const uint4*>(kb + g * 128 + ((2 * t4 + par) << 4));
+            const uint4 kbb = *reinterpret_cast<const uint4*>(kb + g * 128 + ((2 * t4 + 1 - par) << 4));
+            const uint4 kc = *reinterpret_cast<const uint4*>(kb + (g + 8) * 128 + ((2 * t4 + par) << 4));
+            const uint4 kd = *reinterpret_cast<const uint4*>(kb + (g + 8) * 128 + ((2 * t4 + 1 - par) << 4));
+            const uint4 lo0 = par ? kbb : ka, hi0 = par ? ka : kbb, lo8 = par ? kd : kc, hi8 = par ? kc : kd;
+            kr[0] = lo0.x; kr[1] = lo0.y; kr[2] = lo0.z; kr[3] = lo0.w; kr[4] = hi0.x; kr[5] = hi0.y; kr[6] = hi0.z; kr[7] = hi0.w;
+            kr8[0] = lo8.x; kr8[1] = lo8.y; kr8[2] = lo8.z; kr8[3] = lo8.w; kr8[4] = hi8.x; kr8[5] = hi8.y; kr8[6] = hi8.z; kr8[7] = hi8.w;
+#pragma unroll
+            for (int dt = 0; dt < 4; ++dt) {             // V^T block [64 d][16 rows]: rows 4 t4 .. 4 t4 + 3 of d = 16 dt + g (+8)
+                vf[dt][0] = *reinterpret_cast<const uint2*>(vb + (dt * 16 + g) * 32 + 8 * t4);
+                vf[dt][1] = *reinterpret_cast<const uint2*>(vb + (dt * 16 + g + 8) * 32 + 8 * t4);
             }
-            const float mnew = fmaxf(m, fmaxf(s[0], s[1]));
-            if (mnew > -INFINITY) {
-                const float sc = (m == -INFINITY) ? 0.f : exp2f(m - mnew);
-                l *= sc;
+        }
+        cl_release(c);
+        if (mine && p.dbg != 1) {
+            float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] *= sc;
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t a[4] = {kr[2 * ks], kr8[2 * ks], kr[2 * ks + 1], kr8[2 * ks + 1]};
+                mma_bf16_16816(sc, a, qb0[ks], qb1[ks]);
+            }
+            const int r0 = ci * CL_KV_ROWS + g;
+            const float s0 = (t4 == 0 && r0 < vlen) ? sc[0] : -INFINITY;
+            const float s8 = (t4 == 0 && r0 + 8 < vlen) ? sc[2] : -INFINITY;
+            const float mnew = fmaxf(m, warp_max(fmaxf(s0, s8)));
+            if (mnew > -INFINITY) {                      // warp-uniform
+                const float scale = (m == -INFINITY) ? 0.f : exp2f(m - mnew);
+                const float p0 = exp2f(s0 - mnew), p8 = exp2f(s8 - mnew);
+                l = l * scale + p0 + p8;                 // lane-partial sum, reduced once at the end
+                if (t4 == 0) { pscr[g] = p0; pscr[g + 8] = p8; }
+                __syncwarp();
+                const float4 pv = *reinterpret_cast<const float4*>(pscr + 4 * t4);
+                __syncwarp();
+                const uint32_t b0 = g == 0 ? pack_bf16x2(pv.x, pv.y) : 0u, b1 = g == 0 ? pack_bf16x2(pv.z, pv.w) : 0u;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const float pu = exp2f(s[u] - mnew);
-                    l += pu;
-                    const float2 v0 = unpack_bf16x2(vv[u].x), v1 = unpack_bf16x2(vv[u].y), v2 = unpack_bf16x2(vv[u].z), v3 = unpack_bf16x2(vv[u].w);
-                    acc[0] += pu * v0.x; acc[1] += pu * v0.y; acc[2] += pu * v1.x; acc[3] += pu * v1.y;
-                    acc[4] += pu * v2.x; acc[5] += pu * v2.y; acc[6] += pu * v3.x; acc[7] += pu * v3.y;
+                for (int dt = 0; dt < 4; ++dt) {
+                    o[dt][0] *= scale; o[dt][1] *= scale; o[dt][2] *= scale; o[dt][3] *= scale;
+                    const uint32_t a[4] = {vf[dt][0].x, vf[dt][1].x, vf[dt][0].y, vf[dt][1].y};
+                    mma_bf16_16816(o[dt], a, b0, b1);
                 }
                 m = mnew;
             }
         }
-        if (self && c.warp == 0 && g4 == 0) {            // newest row: bf16-rounded k_t, v_t as the cache stores them
-            float ps = 0.f;
+    }
+    if (active) {
+        if (self && par2 == 0) {                         // newest row: bf16-rounded q, k_t, v_t exactly as the MMA path sees them
+            const float* qp = qkv + gi * 192 + 2 * c.lane;
+            const float2 qd = unpack_bf16x2(pack_bf16x2(qp[0] * qs, qp[1] * qs));
+            const float2 kd = unpack_bf16x2(pack_bf16x2(qp[64], qp[65]));
+            const float st = warp_sum(qd.x * kd.x + qd.y * kd.y);
+            const float mnew = fmaxf(m, st);
+            const float scale = (m == -INFINITY) ? 0.f : exp2f(m - mnew), pt = exp2f(st - mnew);
+            l = l * scale + (c.lane == 0 ? pt : 0.f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ps += q[j] * __bfloat162float(__float2bfloat16(qkv[gi * 192 + 64 + sub * 8 + j]));
-            ps += __shfl_xor_sync(0x000000ffu, ps, 1);
-            ps += __shfl_xor_sync(0x000000ffu, ps, 2);
-            ps += __shfl_xor_sync(0x000000ffu, ps, 4);
-            const float mnew = fmaxf(m, ps);
-            const float sc = (m == -INFINITY) ? 0.f : exp2f(m - mnew), pu = exp2f(ps - mnew);
-            l = l * sc + pu;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = acc[j] * sc + pu * __bfloat162float(__float2bfloat16(qkv[gi * 192 + 128 + sub * 8 + j]));
+            for (int dt = 0; dt < 4; ++dt) {
+                const float v0 = __bfloat162float(__float2bfloat16(qkv[gi * 192 + 128 + dt * 16 + g]));
+                const float v8 = __bfloat162float(__float2bfloat16(qkv[gi * 192 + 128 + dt * 16 + g + 8]));
+                o[dt][0] = o[dt][0] * scale + pt * v0;
+                o[dt][2] = o[dt][2] * scale + pt * v8;
+            }
             m = mnew;
         }
-        // merge the 4 row-groups of the warp, then the 16 warps through shared memory
+        // partial (m, l, o[64]) of this warp -> scratch; the even warp of the pair merges the two halves
+        const float ls = warp_sum(l);
+        if (t4 == 0) {
 #pragma unroll
-        for (int off = 8; off <= 16; off <<= 1) {
-            const float mo = __shfl_xor_sync(0xffffffffu, m, off), lo = __shfl_xor_sync(0xffffffffu, l, off);
-            const float mn = fmaxf(m, mo);
-            const float e1 = (m == -INFINITY) ? 0.f : exp2f(m - mn), e2 = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
-            l = l * e1 + lo * e2;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { const float ao = __shfl_xor_sync(0xffffffffu, acc[j], off); acc[j] = acc[j] * e1 + ao * e2; }
-            m = mn;
+            for (int dt = 0; dt < 4; ++dt) { pscr[dt * 16 + g] = o[dt][0]; pscr[dt * 16 + g + 8] = o[dt][2]; }
         }
-        if (c.lane < 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) am[c.warp * 68 + sub * 8 + j] = acc[j];
-            if (c.lane == 0) { am[c.warp * 68 + 64] = m; am[c.warp * 68 + 65] = l; }
-        }
-        consumer_bar();
-        if (c.tid < 64) {
-            float mm = -INFINITY;
-#pragma unroll
-            for (int w = 0; w < CL_WARPS; ++w) mm = fmaxf(mm, am[w * 68 + 64]);
-            float ls = 0.f, o = 0.f;
-#pragma unroll
-            for (int w = 0; w < CL_WARPS; ++w) {
-                const float mw = am[w * 68 + 64];
-                const float e = (mw == -INFINITY) ? 0.f : exp2f(mw - mm);
-                ls += am[w * 68 + 65] * e; o += am[w * 68 + c.tid] * e;
-            }
-            stage[gi * 64 + c.tid] = ls > 0.f ? o / ls : 0.f;
-        }
-        consumer_bar();
+        if (c.lane == 0) { pscr[64] = m; pscr[65] = ls; }
     }
+    consumer_bar();
+    if (active && par2 == 0) {
+        const float* pa = pscr;
+        const float* pb = pscr + 68;
+        const float ma = pa[64], mb = pb[64], mm = fmaxf(ma, mb);
+        const float ea = (ma == -INFINITY) ? 0.f : exp2f(ma - mm), eb = (mb == -INFINITY) ? 0.f : exp2f(mb - mm);
+        const float ls = pa[65] * ea + pb[65] * eb;
+        const float inv = ls > 0.f ? 1.f / ls : 0.f;
+        stage[gi * 64 + c.lane] = (pa[c.lane] * ea + pb[c.lane] * eb) * inv;
+        stage[gi * 64 + 32 + c.lane] = (pa[32 + c.lane] * ea + pb[32 + c.lane] * eb) * inv;
+    }
+    consumer_bar();
     push_bf16_all(c, stage, 64, reinterpret_cast<bf16*>(c.smem + SM_ABUF) + c.rank * 64, LDX512, 64);
 }
 
 // ---------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const ClusterParams p, int t0, int n_steps) {
+__global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __grid_constant__ ClusterParams p, int t0, int n_steps) {
     extern __shared__ __align__(128) unsigned char cl_smem[];
     ClCtx c;
     c.smem = cl_smem;
@@ -449,7 +530,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const Clu
     volatile int* flags = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 128);
     c.rank = (int)cluster_ctarank();
     c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
-    c.sync_phase = 0;
+    c.sync_phase = 0; c.dbg = p.dbg;
     const int cid = (int)cluster_id_x(), ncl = (int)cluster_nid_x();
     const bool is_producer = c.warp == CL_WARPS;
 
@@ -503,34 +584,47 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const Clu
         __syncthreads();
 
         if (is_producer) {
-            if (c.lane == 0 && !skip) cl_producer(p, cl_smem, c.full, c.empty, flags, c.rank, c.b0, c.G, t0, t0 + n_steps);
-            __syncwarp();
+            if (!skip) cl_producer(p, cl_smem, c.full, c.empty, flags, c.rank, c.b0, c.G, t0, t0 + n_steps, c.lane);
         } else if (skip) {
             cl_sync(c); cl_sync(c);
         } else {
-            cl_sync(c);                                  // peers' buffers are initialised before any DSMEM push
+            { const int d = c.dbg; c.dbg = 0; cl_sync(c); c.dbg = d; }   // peers' buffers are initialised before any DSMEM push
+            if (c.dbg >= 5) {                            // profiling experiment: drain the chunk stream, no compute (results invalid)
+                for (int t = t0; t < t0 + n_steps; ++t)
+                    for (int seg = 0; seg <= 51; ++seg) {
+                        const int n = seg_chunks(seg, t, p.S, c.G, c.rank, c.dbg);
+                        for (int i = 0; i < n; ++i) { cl_acquire(c); cl_release(c); }
+                    }
+            } else
             for (int t = t0; t < t0 + n_steps; ++t) {
                 // ================= decoder prenet (dropout always on, P7) =================
-                cl_gemm(c, 1, 2, 2, false, fbuf, LDX128, [&](int ti, int n, int m, float v) {
-                    const int cc = ti * 16 + n, col = c.rank * 32 + cc;
-                    v = fmaxf(v + __ldg(p.b_fc1 + col), 0.f);
-                    stg[m * 32 + cc] = keep_bit(p.seed, SITE_DEC_PRENET_FC1, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
-                });
+                LnAffine lna;
+                cl_gemm(c, 1, 2, 2, false, fbuf, LDX128,
+                        [&](int ti, int n) { return __ldg(p.b_fc1 + c.rank * 32 + ti * 16 + n); },
+                        [&](int ti, int n, int m, float v) {
+                            const int cc = ti * 16 + n, col = c.rank * 32 + cc;
+                            v = fmaxf(v, 0.f);
+                            stg[m * 32 + cc] = keep_bit(p.seed, SITE_DEC_PRENET_FC1, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
+                        });
                 push_bf16_all(c, stg, 32, h1 + c.rank * 32, LDX256, 32);
                 cl_sync(c);
                 stamp(t, 0);
-                cl_gemm(c, 1, 2, 4, false, h1, LDX256, [&](int ti, int n, int m, float v) {
-                    const int cc = ti * 16 + n, col = c.rank * 32 + cc;
-                    v = fmaxf(v + __ldg(p.b_fc2 + col), 0.f);
-                    stg[m * 32 + cc] = keep_bit(p.seed, SITE_DEC_PRENET_FC2, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
-                });
+                cl_gemm(c, 1, 2, 4, false, h1, LDX256,
+                        [&](int ti, int n) { return __ldg(p.b_fc2 + c.rank * 32 + ti * 16 + n); },
+                        [&](int ti, int n, int m, float v) {
+                            const int cc = ti * 16 + n, col = c.rank * 32 + cc;
+                            v = fmaxf(v, 0.f);
+                            stg[m * 32 + cc] = keep_bit(p.seed, SITE_DEC_PRENET_FC2, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
+                        });
                 push_bf16_all(c, stg, 32, h2 + c.rank * 32, LDX256, 32);
                 cl_sync(c);
                 stamp(t, 1);
-                cl_gemm(c, 1, 4, 4, false, h2, LDX256, [&](int ti, int n, int m, float v) {
-                    const int cc = ti * 16 + n, col = c.rank * CL_NS + cc;
-                    stg[m * CL_NS + cc] = v + __ldg(p.b_proj + col) + p.dec_alpha * __ldg(p.pe + (size_t)t * kDModel + col);
-                });
+                cl_gemm(c, 1, 4, 4, false, h2, LDX256,
+                        [&](int ti, int n) {
+                            const int col = c.rank * CL_NS + ti * 16 + n;
+                            return __ldg(p.b_proj + col) + p.dec_alpha * __ldg(p.pe + (size_t)t * kDModel + col);
+                        },
+                        [&](int ti, int n, int m, float v) { stg[m * CL_NS + ti * 16 + n] = v; });
                 push_f32_all(c, stg, CL_NS, xres + c.rank * CL_NS, 512, CL_NS);
                 push_bf16_all(c, stg, CL_NS, xa + c.rank * CL_NS, LDX512, CL_NS);
                 cl_sync(c);
@@ -539,65 +633,78 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const Clu
                 for (int l = 0; l < 6; ++l) {
                     const ClusterLayerParams& W = p.layer[l];
                     // ---- q, k, v of head `rank` for every row of the group (local; k_t, v_t appended to the cache)
-                    cl_gemm(c, 8, 12, 1, false, xa, LDX512, [&](int ti, int n, int m, float v) {
-                        const int cc = ti * 16 + n, part = cc >> 6, dd = cc & 63;
-                        v += __ldg(W.bqkv + part * 512 + c.rank * 64 + dd);
-                        qkvb[m * 192 + cc] = v;
-                        if (part > 0) {
-                            const size_t idx = ((((size_t)(l * 2 + part - 1) * p.B + c.b0 + m) * kHeads + c.rank) * p.Tmax + t) * kDHead + dd;
-                            p.self_kv[idx] = __float2bfloat16(v);
-                        }
-                    });
+                    cl_gemm(c, 8, 12, 1, false, xa, LDX512,
+                            [&](int ti, int n) { const int cc = ti * 16 + n; return __ldg(W.bqkv + (cc >> 6) * 512 + c.rank * 64 + (cc & 63)); },
+                            [&](int ti, int n, int m, float v) {
+                                const int cc = ti * 16 + n, part = cc >> 6, dd = cc & 63;
+                                qkvb[m * 192 + cc] = v;
+                                if (part > 0) {               // append to the cache: K row-major, V in transposed 16-row blocks
+                                    const size_t pbase = (((size_t)(l * 2 + part - 1) * p.B + c.b0 + m) * kHeads + c.rank) * p.Tpad * kDHead;
+                                    const size_t off = part == 1 ? (size_t)t * kDHead + dd : (size_t)(t >> 4) * 1024 + dd * 16 + (t & 15);
+                                    p.self_kv[pbase + off] = __float2bfloat16(v);
+                                }
+                            });
+                    // the appended rows are read by the async proxy (TMA copies) from the next step on: order the
+                    // generic-proxy stores before them here, on the writer side (a fence next to every copy would
+                    // serialise the producer's copies); the ring's empty/full mbarriers carry the rest of the ordering
+                    asm volatile("fence.proxy.async;" ::: "memory");
                     stamp(t, 3 + 8 * l);
                     cl_attention(p, c, true, t, stg);
                     cl_sync(c);
                     stamp(t, 4 + 8 * l);
                     // ---- O projection + residual, gathered -> LayerNorm 1
-                    cl_gemm(c, 2, 4, 4, false, abuf, LDX512, [&](int ti, int n, int m, float v) {
-                        const int cc = ti * 16 + n, col = c.rank * CL_NS + cc;
-                        stg[m * CL_NS + cc] = v + __ldg(W.bo + col) + xres[m * 512 + col];
-                    });
+                    cl_gemm(c, 2, 4, 4, false, abuf, LDX512,
+                            [&](int ti, int n) { return __ldg(W.bo + c.rank * CL_NS + ti * 16 + n); },
+                            [&](int ti, int n, int m, float v) {
+                                const int cc = ti * 16 + n;
+                                stg[m * CL_NS + cc] = v + xres[m * 512 + c.rank * CL_NS + cc];
+                            });
                     push_f32_all(c, stg, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
+                    ln_prefetch(c, W.ln1g, W.ln1b, lna);
                     cl_sync(c);
-                    cl_layernorm(c, W.ln1g, W.ln1b);
+                    cl_layernorm(c, lna);
                     stamp(t, 5 + 8 * l);
                     // ---- cross-attention query of head `rank` (local)
-                    cl_gemm(c, 2, 4, 4, false, xa, LDX512, [&](int ti, int n, int m, float v) {
-                        const int cc = ti * 16 + n;
-                        qkvb[m * 192 + cc] = v + __ldg(W.bq2 + c.rank * CL_NS + cc);
-                    });
+                    cl_gemm(c, 2, 4, 4, false, xa, LDX512,
+                            [&](int ti, int n) { return __ldg(W.bq2 + c.rank * CL_NS + ti * 16 + n); },
+                            [&](int ti, int n, int m, float v) { qkvb[m * 192 + ti * 16 + n] = v; });
                     stamp(t, 6 + 8 * l);
                     cl_attention(p, c, false, t, stg);
                     cl_sync(c);
                     stamp(t, 7 + 8 * l);
-                    cl_gemm(c, 2, 4, 4, false, abuf, LDX512, [&](int ti, int n, int m, float v) {
-                        const int cc = ti * 16 + n, col = c.rank * CL_NS + cc;
-                        stg[m * CL_NS + cc] = v + __ldg(W.bo2 + col) + xres[m * 512 + col];
-                    });
+                    cl_gemm(c, 2, 4, 4, false, abuf, LDX512,
+                            [&](int ti, int n) { return __ldg(W.bo2 + c.rank * CL_NS + ti * 16 + n); },
+                            [&](int ti, int n, int m, float v) {
+                                const int cc = ti * 16 + n;
+                                stg[m * CL_NS + cc] = v + xres[m * 512 + c.rank * CL_NS + cc];
+                            });
                     push_f32_all(c, stg, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
+                    ln_prefetch(c, W.ln2g, W.ln2b, lna);
                     cl_sync(c);
-                    cl_layernorm(c, W.ln2g, W.ln2b);
+                    cl_layernorm(c, lna);
                     stamp(t, 8 + 8 * l);
                     // ---- FFN: hidden slice [256 rank, +256) stays local (bf16); FFN2 is split along K
-                    cl_gemm(c, 8, 16, 1, false, xa, LDX512, [&](int ti, int n, int m, float v) {
-                        const int cc = ti * 16 + n;
-                        hbuf[m * LDX256 + cc] = __float2bfloat16(fmaxf(v + __ldg(W.b1 + c.rank * 256 + cc), 0.f));
-                    });
+                    cl_gemm(c, 8, 16, 1, false, xa, LDX512,
+                            [&](int ti, int n) { return __ldg(W.b1 + c.rank * 256 + ti * 16 + n); },
+                            [&](int ti, int n, int m, float v) { hbuf[m * LDX256 + ti * 16 + n] = __float2bfloat16(fmaxf(v, 0.f)); });
                     stamp(t, 9 + 8 * l);
                     // partial sums over this rank's 256 hidden units, staged in ybuf (free between LN2 and the y3 gather)
-                    cl_gemm(c, 8, 32, 1, true, hbuf, LDX256, [&](int ti, int n, int m, float v) { ybuf[m * 512 + ti * 16 + n] = v; });
+                    cl_gemm(c, 8, 32, 1, true, hbuf, LDX256, [&](int, int) { return 0.f; },
+                            [&](int ti, int n, int m, float v) { ybuf[m * 512 + ti * 16 + n] = v; });
                     for (int i = c.tid; i < CL_SIZE * c.G * 16; i += CL_CONSUMERS) {   // reduce-scatter: 64 columns to each peer
                         const int peer = i / (c.G * 16), j = i % (c.G * 16), m = j >> 4, pc = j & 15;
                         const float4 v = *reinterpret_cast<const float4*>(ybuf + m * 512 + peer * CL_NS + pc * 4);
                         st_cluster_v4(map_to_rank(smem_u32(recv + (c.rank * 8 + m) * CL_NS + pc * 4), (uint32_t)peer),
                                       __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
                     }
+                    const float b2v = __ldg(W.b2 + c.rank * CL_NS + (c.tid & 63));
+                    ln_prefetch(c, W.ln3g, W.ln3b, lna);
                     cl_sync(c);
                     {
                         float* st2 = reinterpret_cast<float*>(c.smem + SM_RED);    // [8][64] staging of my reduced columns
                         const int m = c.tid >> 6, cc = c.tid & 63, col = c.rank * CL_NS + cc;
                         if (m < c.G) {
-                            float v = __ldg(W.b2 + col) + xres[m * 512 + col];
+                            float v = b2v + xres[m * 512 + col];
 #pragma unroll
                             for (int r = 0; r < CL_SIZE; ++r) v += recv[(r * 8 + m) * CL_NS + cc];    // fixed order
                             st2[m * CL_NS + cc] = v;
@@ -606,26 +713,27 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const Clu
                         push_f32_all(c, st2, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
                     }
                     cl_sync(c);
-                    cl_layernorm(c, W.ln3g, W.ln3b);
+                    cl_layernorm(c, lna);
                     stamp(t, 10 + 8 * l);
                 }
                 // ================= [mel | stop] heads: ranks 0..5 own 16 of the 81(+15) columns =================
                 if (c.rank < 6) {
-                    cl_gemm(c, 1, 1, 8, false, xa, LDX512, [&](int, int n, int m, float v) {
-                        const int col = c.rank * 16 + n, b = c.b0 + m;
-                        if (col <= 80) v += __ldg(p.b_head + col);
-                        if (col < 80) p.mel_before[((size_t)b * p.Tmax + t) * 80 + col] = v;   // fp32 feedback (P8)
-                        else if (col == 80) {
-                            p.stop_logits[(size_t)b * p.Tmax + t] = v;
-                            if (v > 0.f && p.finished[b] == 0) {                         // P10
-                                p.finished[b] = 1; p.lens[b] = t + 1; atomicAdd(p.n_finished, 1);
-                                const uint32_t fa = smem_u32(const_cast<int*>(flags));
+                    cl_gemm(c, 1, 1, 8, false, xa, LDX512,
+                            [&](int, int n) { const int col = c.rank * 16 + n; return col <= 80 ? __ldg(p.b_head + col) : 0.f; },
+                            [&](int, int n, int m, float v) {
+                                const int col = c.rank * 16 + n, b = c.b0 + m;
+                                if (col < 80) p.mel_before[((size_t)b * p.Tmax + t) * 80 + col] = v;   // fp32 feedback (P8)
+                                else if (col == 80) {
+                                    p.stop_logits[(size_t)b * p.Tmax + t] = v;
+                                    if (v > 0.f && p.finished[b] == 0) {                         // P10
+                                        p.finished[b] = 1; p.lens[b] = t + 1; atomicAdd(p.n_finished, 1);
+                                        const uint32_t fa = smem_u32(const_cast<int*>(flags));
 #pragma unroll
-                                for (int r = 0; r < CL_SIZE; ++r) red_cluster_add_u32(map_to_rank(fa, r), 1u);
-                            }
-                        }
-                        stg[m * 16 + n] = v;
-                    });
+                                        for (int r = 0; r < CL_SIZE; ++r) red_cluster_add_u32(map_to_rank(fa, r), 1u);
+                                    }
+                                }
+                                stg[m * 16 + n] = v;
+                            });
                     if (c.rank < 5) push_bf16_all(c, stg, 16, fbuf + c.rank * 16, LDX128, 16);   // the frame = next step's prenet input
                 }
                 cl_sync(c);
@@ -635,7 +743,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const Clu
             // ---- tell the producer we are done; peers finish the group before anyone re-initialises buffers
             consumer_bar();
             if (c.tid == 0) { flags[2] = (int)c.consumed; __threadfence_block(); flags[1] = 1; }
-            cl_sync(c);
+            { const int d = c.dbg; c.dbg = 0; cl_sync(c); c.dbg = d; }
         }
         __syncthreads();                                 // producer has drained the ring
     }

@@ -10,7 +10,7 @@
 namespace tts {
 
 enum GemmAct { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
-enum GemmScatter { SC_NONE = 0, SC_CROSS_KV = 1, SC_HEAD = 2 };
+enum GemmScatter { SC_NONE = 0, SC_CROSS_KV = 1, SC_HEAD = 2, SC_CROSS_KV_VT = 3 };
 
 struct GemmParams {
     // operands
@@ -30,6 +30,7 @@ struct GemmParams {
     // SC_CROSS_KV: out_bf16 = cache [layers][2][B][H][S][64], N = layers * 1024, T = S
     // SC_HEAD    : out_f32 = mel_before [M][80], out2_f32 = stop_logits [M]
     float* out2_f32; int B;
+    int Lpad;                        // SC_CROSS_KV*: row capacity of the cache per (layer, kv, b, h), multiple of 16
 };
 
 constexpr int GB_M = 128, GB_N = 128, GB_K = 32, G_STAGES = 3, G_LDS = GB_K + 8;   // smem row = 40 bf16 = 80 B
@@ -60,11 +61,19 @@ TTS_D void gemm_store(const GemmParams& p, int m, int n, float v0, float v1) {
         if (has1) v1 = keep_bit(p.seed, p.drop_site, t, p.utt_offset + b, n + 1) ? 2.f * v1 : 0.f;
     }
     if (p.lens && t >= p.lens[b]) { v0 = 0.f; v1 = 0.f; }
-    if (p.scatter == SC_CROSS_KV) {
-        // n = layer * 1024 + kv * 512 + h * 64 + d  ->  [layer][kv][B][H][S=T][64]
+    if (p.scatter == SC_CROSS_KV || p.scatter == SC_CROSS_KV_VT) {
+        // n = layer * 1024 + kv * 512 + h * 64 + d  ->  cache [layer][kv][B][H][Lpad * 64]; K rows are row-major, V is
+        // row-major too (SC_CROSS_KV, teacher-forced flash attention) or in transposed 16-row blocks
+        // [Lpad/16][64 d][16 rows] (SC_CROSS_KV_VT, decode_cluster.cuh)
         const int lkv = n >> 9, h = (n >> 6) & 7, d = n & 63;
-        size_t idx = ((((size_t)lkv * p.B + b) * kHeads + h) * p.T + t) * kDHead + d;
-        *reinterpret_cast<uint32_t*>(p.out_bf16 + idx) = pack_bf16x2(v0, v1);
+        const size_t base = (((size_t)lkv * p.B + b) * kHeads + h) * (size_t)p.Lpad * kDHead;
+        if (p.scatter == SC_CROSS_KV_VT && (lkv & 1)) {
+            bf16* blk = p.out_bf16 + base + (size_t)(t >> 4) * 1024 + (t & 15);
+            blk[d * 16] = __float2bfloat16(v0);
+            blk[(d + 1) * 16] = __float2bfloat16(v1);
+        } else {
+            *reinterpret_cast<uint32_t*>(p.out_bf16 + base + (size_t)t * kDHead + d) = pack_bf16x2(v0, v1);
+        }
         return;
     }
     if (p.scatter == SC_HEAD) {

@@ -89,12 +89,10 @@ __global__ void mask_rows_kernel(float* __restrict__ x, const int* __restrict__ 
     if (t >= lens[b]) x[i] = 0.f;
 }
 
-__global__ void init_decode_state_kernel(int* lens, int* finished, int* scalars /*n_finished,t_done,barrier,pad*/,
-                                         unsigned* part_cnt, int B, int max_len, int n_pairs) {
+__global__ void init_decode_state_kernel(int* lens, int* finished, int* scalars /*n_finished, ...*/, int B, int max_len) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) { lens[i] = max_len; finished[i] = 0; }
     if (i < 4) scalars[i] = 0;
-    if (i < n_pairs) part_cnt[i] = 0u;
 }
 
 __global__ void philox_bits_kernel(uint64_t seed, int site, int T, int B, int C, int utt_offset, uint8_t* out) {

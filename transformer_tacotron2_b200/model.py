@@ -129,7 +129,6 @@ class TransformerTTS(nn.Module):
         self._lib = None
         self._handle = C.c_void_p()
         self._dirty = True
-        self._persistent = True
         self.profile_events = False      # bench.py: CUDA-event time of the decode loop per inference()
         self.decode_ms = []
         self._ws = None
@@ -162,8 +161,6 @@ class TransformerTTS(nn.Module):
     def set_option(self, key: str, value: int):
         lib = self._ensure_handle()
         self._check(lib.tts_set_option(self._handle, key.encode(), int(value)), "tts_set_option")
-        if key == "decode_persistent":
-            self._persistent = bool(value)
 
     def sync_weights(self):
         """Push the module's parameters through tts_load_weight / tts_finalize_weights."""
@@ -269,7 +266,7 @@ class TransformerTTS(nn.Module):
         self._check(lib.tts_decode_begin(self._handle, ws.data_ptr(), B, S, int(max_len), int(seed), u0, stream), "tts_decode_begin")
         self._check(lib.tts_encode(self._handle, ws.data_ptr(), ph.data_ptr(), pl.data_ptr(), B, S, int(max_len), None, stream), "tts_encode")
         td, nf = C.c_int(0), C.c_int(0)
-        chunk = int(max_len) if self._persistent else 16   # the persistent kernel stops itself on the device
+        chunk = int(max_len)                               # one launch: every cluster stops itself on the device
         if self.profile_events:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(torch.cuda.current_stream(dev))
@@ -289,10 +286,6 @@ class TransformerTTS(nn.Module):
         rc = lib.tts_decode_end(self._handle, ws.data_ptr(), T, ma.data_ptr(), ml.data_ptr(), st.data_ptr(),
                                 mb.data_ptr() if return_before else None, stream)
         self._check(rc, "tts_decode_end")
-        if not self._persistent and nf.value >= B:         # per-phase launches overshoot in chunks of 16 steps
-            T = int(ml.max())
-            ma, st = ma[:, :T].contiguous(), st[:, :T].contiguous()
-            mb = mb[:, :T].contiguous() if return_before else None
         if return_before:
             return ma, ml, st, mb
         return ma, ml, st
@@ -304,6 +297,7 @@ class TransformerTTS(nn.Module):
         if n <= 0:
             raise _lib.TtsError(f"tts_debug_phase_timestamps failed ({n})")
         self.debug_stamps = out[n_steps].clone()
+        self.all_stamps = out[:n_steps].clone()            # incl. ad-hoc profiling columns 52..63
         return out[:n_steps, :n].clone()
 
     @torch.no_grad()

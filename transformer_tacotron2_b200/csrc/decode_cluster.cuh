@@ -54,7 +54,7 @@ constexpr int SM_H2 = SM_H1 + 4224;
 constexpr int SM_FBUF = SM_H2 + 4224;                           // bf16 [8][136] previous frame (K padded to 128)
 constexpr int SM_AMERGE = SM_FBUF + 2176;                       // f32 [16][68]  attention warp partials
 constexpr int SM_MISC = SM_AMERGE + 4352;                       // mbarriers + flags
-constexpr int CL_SMEM_BYTES = SM_MISC + 256;
+constexpr int CL_SMEM_BYTES = SM_MISC + 320;             // barriers (128) + flags (32) + 8 head records (128)
 constexpr int LDX512 = 520, LDX256 = 264, LDX128 = 136;
 
 struct ClusterLayerParams {
@@ -130,11 +130,12 @@ TTS_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, u
 // ---------------------------------------------------------------- per-CTA context (consumer side)
 struct ClCtx {
     unsigned char* smem;
-    uint64_t *full, *empty, *csync;
+    uint64_t *full, *empty, *csync, *gsync;   // ring full/empty, classic cluster barrier, data-carrying gather barriers [2]
     int rank, tid, warp, lane;
     int b0, G;                           // group base utterance, rows in this group
     uint32_t consumed;                   // chunks consumed (uniform over the consumer warps)
     uint32_t sync_phase;                 // cluster barrier phase counter
+    uint32_t gphase;                     // gather phase counter (40 per decoder step)
     int dbg;
 };
 
@@ -327,44 +328,78 @@ TTS_D void cl_gemm(ClCtx& c, int nchunks, int NT, int KSPLIT, bool typeB, const 
     }
 }
 
-// ---- DSMEM pushes: 16-byte st.shared::cluster stores from a local f32 staging tile [G][ld] -----------------
+// ---- DSMEM pushes that carry their own completion ---------------------------------------------------------------
+// Every exchange of the step ("gather phase") is a set of 16-byte st.async stores into the peers' shared memory, each
+// of which completes 16 bytes of a transaction count on the RECEIVER's mbarrier: the receiver waits for the expected
+// byte count of the phase instead of a separate arrive/wait round after the data (one DSMEM latency instead of
+// two-and-a-half).  Two barriers alternate (a peer can be at most one phase ahead, because every rank contributes to
+// every phase); barrier k&1 is re-armed for phase k+2 the moment phase k completes, so data never precedes its arming.
+TTS_D void st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c2, uint32_t d, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+                 ::"r"(addr), "r"(a), "r"(b), "r"(c2), "r"(d), "r"(remote_bar) : "memory");
+}
+// expected bytes of gather phase ph (0..39 within a step) at every receiver
+TTS_D uint32_t gather_bytes(int ph, int G) {
+    if (ph < 2) return 512u * G;                         // prenet fc1 / fc2: 8 ranks x G x 32 cols bf16
+    if (ph == 2) return 3072u * G;                       // prenet proj: 8 x G x 64 x (f32 + bf16)
+    if (ph == 39) return 160u * G + 128u;                // head: 5 ranks x G x 16 cols bf16 + one 16-byte record per rank
+    const int k = (ph - 3) % 6;
+    return (k == 0 || k == 2) ? 1024u * G : 2048u * G;   // attention outputs (bf16) : f32 slices (O, O2, reduce-scatter, y3)
+}
+TTS_D uint32_t gather_bar(const ClCtx& c) { return smem_u32(&c.gsync[c.gphase & 1]); }
+TTS_D void cl_sync(ClCtx& c);
+TTS_D void gather_wait(ClCtx& c) {
+    if (c.dbg == 8) { cl_sync(c); ++c.gphase; return; }   // experiment: classic push + arrive/wait barrier
+    uint64_t* bar = &c.gsync[c.gphase & 1];
+    if (c.dbg != 3) mbar_wait(bar, (c.gphase >> 1) & 1);
+    if (c.tid == 0) mbar_expect_tx(bar, gather_bytes((int)((c.gphase + 2) % 40), c.G));
+    ++c.gphase;
+}
 // dst (f32, row stride dld) of every peer <- stage[m][0..ncols)
 TTS_D void push_f32_all(const ClCtx& c, const float* stage, int ld, float* dst, int dld, int ncols) {
     const int ppr = ncols >> 2, per_peer = c.G * ppr;
+    const uint32_t bar = gather_bar(c);
     for (int i = c.tid; i < per_peer * CL_SIZE; i += CL_CONSUMERS) {
         const int peer = i / per_peer, j = i % per_peer, m = j / ppr, pc = j - m * ppr;
         const float4 v = *reinterpret_cast<const float4*>(stage + m * ld + pc * 4);
-        st_cluster_v4(map_to_rank(smem_u32(dst + m * dld + pc * 4), (uint32_t)peer),
-                      __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+        if (c.dbg == 8) st_cluster_v4(map_to_rank(smem_u32(dst + m * dld + pc * 4), (uint32_t)peer), __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+        else
+        st_async_v4(map_to_rank(smem_u32(dst + m * dld + pc * 4), (uint32_t)peer),
+                    __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w), map_to_rank(bar, (uint32_t)peer));
     }
 }
 // dst (bf16, row stride dld) of every peer <- bf16(stage[m][0..ncols)), ncols % 8 == 0
 TTS_D void push_bf16_all(const ClCtx& c, const float* stage, int ld, bf16* dst, int dld, int ncols) {
     const int ppr = ncols >> 3, per_peer = c.G * ppr;
+    const uint32_t bar = gather_bar(c);
     for (int i = c.tid; i < per_peer * CL_SIZE; i += CL_CONSUMERS) {
         const int peer = i / per_peer, j = i % per_peer, m = j / ppr, pc = j - m * ppr;
         const float4 v0 = *reinterpret_cast<const float4*>(stage + m * ld + pc * 8);
         const float4 v1 = *reinterpret_cast<const float4*>(stage + m * ld + pc * 8 + 4);
-        st_cluster_v4(map_to_rank(smem_u32(dst + m * dld + pc * 8), (uint32_t)peer),
-                      pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+        if (c.dbg == 8) st_cluster_v4(map_to_rank(smem_u32(dst + m * dld + pc * 8), (uint32_t)peer), pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+        else
+        st_async_v4(map_to_rank(smem_u32(dst + m * dld + pc * 8), (uint32_t)peer),
+                    pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w), map_to_rank(bar, (uint32_t)peer));
     }
 }
 
-// LayerNorm of the gathered rows: ybuf -> xres (f32) + xa (bf16); warp m < G owns row m.  The affine
-// parameters (global memory) are fetched by ln_prefetch() BEFORE the cluster barrier the rows are waited on.
-struct LnAffine { float4 g[4], b[4]; };
-TTS_D void ln_prefetch(const ClCtx& c, const float* g, const float* b, LnAffine& a) {
-    if (c.warp < c.G) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            a.g[i] = __ldg(reinterpret_cast<const float4*>(g + i * 128 + c.lane * 4));
-            a.b[i] = __ldg(reinterpret_cast<const float4*>(b + i * 128 + c.lane * 4));
-        }
+// LayerNorm of the gathered rows: ybuf -> xres (f32) + xa (bf16); warp m < G owns row m.  The affine parameters
+// (global memory) are fetched asynchronously into shared memory by ln_prefetch() BEFORE the exchange the rows are
+// waited on (buffer: the prenet's h1 region, idle while the layers run).
+TTS_D void ln_prefetch(const ClCtx& c, const float* g, const float* b) {
+    float* dst = reinterpret_cast<float*>(c.smem + SM_H1);               // [0,512) gamma, [512,1024) beta
+    if (c.tid < 256) {
+        const float* src = (c.tid < 128 ? g : b) + (c.tid & 127) * 4;
+        cp_async_16(dst + c.tid * 4, src, true);
     }
+    cp_async_commit();
 }
-TTS_D void cl_layernorm(ClCtx& c, const LnAffine& a) {
+TTS_D void cl_layernorm(ClCtx& c) {
+    cp_async_wait<0>();
+    consumer_bar();
     if (c.warp < c.G && c.dbg != 4) {
         const float* y = reinterpret_cast<const float*>(c.smem + SM_YBUF) + c.warp * 512;
+        const float* gb = reinterpret_cast<const float*>(c.smem + SM_H1);
         float* xr = reinterpret_cast<float*>(c.smem + SM_XRES) + c.warp * 512;
         bf16* xa = reinterpret_cast<bf16*>(c.smem + SM_XA) + c.warp * LDX512;
         float v[16];
@@ -384,8 +419,9 @@ TTS_D void cl_layernorm(ClCtx& c, const LnAffine& a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int col = i * 128 + c.lane * 4;
-            const float o0 = (v[i * 4] - mean) * rstd * a.g[i].x + a.b[i].x, o1 = (v[i * 4 + 1] - mean) * rstd * a.g[i].y + a.b[i].y;
-            const float o2 = (v[i * 4 + 2] - mean) * rstd * a.g[i].z + a.b[i].z, o3 = (v[i * 4 + 3] - mean) * rstd * a.g[i].w + a.b[i].w;
+            const float4 g4 = *reinterpret_cast<const float4*>(gb + col), b4 = *reinterpret_cast<const float4*>(gb + 512 + col);
+            const float o0 = (v[i * 4] - mean) * rstd * g4.x + b4.x, o1 = (v[i * 4 + 1] - mean) * rstd * g4.y + b4.y;
+            const float o2 = (v[i * 4 + 2] - mean) * rstd * g4.z + b4.z, o3 = (v[i * 4 + 3] - mean) * rstd * g4.w + b4.w;
             *reinterpret_cast<float4*>(xr + col) = make_float4(o0, o1, o2, o3);
             *reinterpret_cast<uint2*>(xa + col) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
         }
@@ -526,8 +562,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
     c.full = reinterpret_cast<uint64_t*>(cl_smem + SM_MISC);
     c.empty = c.full + CL_STAGES;
     c.csync = c.empty + CL_STAGES;
-    // flags[0] finished utterances of the group, [1] consumers done (producer stop), [2] final consumed count
+    c.gsync = c.csync + 1;
+    // flags[0] finished utterances of the group (rank 5 counts), [1] consumers done (producer stop), [2] final consumed count
+    // hrec: one 16-byte record per rank, pushed in the head phase (rank 5: finished count)
     volatile int* flags = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 128);
+    volatile int* hrec = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 128 + 32);     // [8 ranks][4]
     c.rank = (int)cluster_ctarank();
     c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
     c.sync_phase = 0; c.dbg = p.dbg;
@@ -567,7 +606,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
             for (int i = c.tid; i < (SM_MISC - SM_XRES) / 4; i += CL_CONSUMERS) reinterpret_cast<uint32_t*>(cl_smem + SM_XRES)[i] = 0u;
         if (c.tid == 0) {
             for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&c.full[s], 1); mbar_init(&c.empty[s], CL_WARPS); }
+            mbar_init(&c.gsync[0], 1); mbar_init(&c.gsync[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&c.gsync[0], gather_bytes(0, c.G));          // phases 0 and 1 are armed before the start barrier
+            mbar_expect_tx(&c.gsync[1], gather_bytes(1, c.G));
             int nf = 0;
             for (int m = 0; m < c.G; ++m) nf += p.finished[c.b0 + m];
             flags[0] = nf; flags[1] = 0; flags[2] = 0;
@@ -579,7 +621,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                 fbuf[m * LDX128 + col] = __float2bfloat16(p.mel_before[((size_t)(c.b0 + m) * p.Tmax + (t0 - 1)) * 80 + col]);
             }
         }
-        c.consumed = 0;
+        c.consumed = 0; c.gphase = 0;
         const bool skip = flags[0] >= c.G;               // every utterance of the group already finished
         __syncthreads();
 
@@ -598,7 +640,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
             } else
             for (int t = t0; t < t0 + n_steps; ++t) {
                 // ================= decoder prenet (dropout always on, P7) =================
-                LnAffine lna;
                 cl_gemm(c, 1, 2, 2, false, fbuf, LDX128,
                         [&](int ti, int n) { return __ldg(p.b_fc1 + c.rank * 32 + ti * 16 + n); },
                         [&](int ti, int n, int m, float v) {
@@ -607,7 +648,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                             stg[m * 32 + cc] = keep_bit(p.seed, SITE_DEC_PRENET_FC1, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
                         });
                 push_bf16_all(c, stg, 32, h1 + c.rank * 32, LDX256, 32);
-                cl_sync(c);
+                gather_wait(c);
+                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                 stamp(t, 0);
                 cl_gemm(c, 1, 2, 4, false, h1, LDX256,
                         [&](int ti, int n) { return __ldg(p.b_fc2 + c.rank * 32 + ti * 16 + n); },
@@ -617,7 +659,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                             stg[m * 32 + cc] = keep_bit(p.seed, SITE_DEC_PRENET_FC2, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
                         });
                 push_bf16_all(c, stg, 32, h2 + c.rank * 32, LDX256, 32);
-                cl_sync(c);
+                gather_wait(c);
+                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                 stamp(t, 1);
                 cl_gemm(c, 1, 4, 4, false, h2, LDX256,
                         [&](int ti, int n) {
@@ -627,7 +670,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         [&](int ti, int n, int m, float v) { stg[m * CL_NS + ti * 16 + n] = v; });
                 push_f32_all(c, stg, CL_NS, xres + c.rank * CL_NS, 512, CL_NS);
                 push_bf16_all(c, stg, CL_NS, xa + c.rank * CL_NS, LDX512, CL_NS);
-                cl_sync(c);
+                gather_wait(c);
+                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                 stamp(t, 2);
 
                 for (int l = 0; l < 6; ++l) {
@@ -650,7 +694,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     asm volatile("fence.proxy.async;" ::: "memory");
                     stamp(t, 3 + 8 * l);
                     cl_attention(p, c, true, t, stg);
-                    cl_sync(c);
+                    gather_wait(c);
+                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                     stamp(t, 4 + 8 * l);
                     // ---- O projection + residual, gathered -> LayerNorm 1
                     cl_gemm(c, 2, 4, 4, false, abuf, LDX512,
@@ -659,10 +704,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                                 const int cc = ti * 16 + n;
                                 stg[m * CL_NS + cc] = v + xres[m * 512 + c.rank * CL_NS + cc];
                             });
+                    ln_prefetch(c, W.ln1g, W.ln1b);
                     push_f32_all(c, stg, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
-                    ln_prefetch(c, W.ln1g, W.ln1b, lna);
-                    cl_sync(c);
-                    cl_layernorm(c, lna);
+                    gather_wait(c);
+                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
+                    cl_layernorm(c);
                     stamp(t, 5 + 8 * l);
                     // ---- cross-attention query of head `rank` (local)
                     cl_gemm(c, 2, 4, 4, false, xa, LDX512,
@@ -670,7 +716,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                             [&](int ti, int n, int m, float v) { qkvb[m * 192 + ti * 16 + n] = v; });
                     stamp(t, 6 + 8 * l);
                     cl_attention(p, c, false, t, stg);
-                    cl_sync(c);
+                    gather_wait(c);
+                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                     stamp(t, 7 + 8 * l);
                     cl_gemm(c, 2, 4, 4, false, abuf, LDX512,
                             [&](int ti, int n) { return __ldg(W.bo2 + c.rank * CL_NS + ti * 16 + n); },
@@ -678,10 +725,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                                 const int cc = ti * 16 + n;
                                 stg[m * CL_NS + cc] = v + xres[m * 512 + c.rank * CL_NS + cc];
                             });
+                    ln_prefetch(c, W.ln2g, W.ln2b);
                     push_f32_all(c, stg, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
-                    ln_prefetch(c, W.ln2g, W.ln2b, lna);
-                    cl_sync(c);
-                    cl_layernorm(c, lna);
+                    gather_wait(c);
+                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
+                    cl_layernorm(c);
                     stamp(t, 8 + 8 * l);
                     // ---- FFN: hidden slice [256 rank, +256) stays local (bf16); FFN2 is split along K
                     cl_gemm(c, 8, 16, 1, false, xa, LDX512,
@@ -691,15 +739,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     // partial sums over this rank's 256 hidden units, staged in ybuf (free between LN2 and the y3 gather)
                     cl_gemm(c, 8, 32, 1, true, hbuf, LDX256, [&](int, int) { return 0.f; },
                             [&](int ti, int n, int m, float v) { ybuf[m * 512 + ti * 16 + n] = v; });
-                    for (int i = c.tid; i < CL_SIZE * c.G * 16; i += CL_CONSUMERS) {   // reduce-scatter: 64 columns to each peer
-                        const int peer = i / (c.G * 16), j = i % (c.G * 16), m = j >> 4, pc = j & 15;
-                        const float4 v = *reinterpret_cast<const float4*>(ybuf + m * 512 + peer * CL_NS + pc * 4);
-                        st_cluster_v4(map_to_rank(smem_u32(recv + (c.rank * 8 + m) * CL_NS + pc * 4), (uint32_t)peer),
-                                      __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+                    {
+                        const uint32_t bar = gather_bar(c);
+                        for (int i = c.tid; i < CL_SIZE * c.G * 16; i += CL_CONSUMERS) {   // reduce-scatter: 64 columns to each peer
+                            const int peer = i / (c.G * 16), j = i % (c.G * 16), m = j >> 4, pc = j & 15;
+                            const float4 v = *reinterpret_cast<const float4*>(ybuf + m * 512 + peer * CL_NS + pc * 4);
+                            if (c.dbg == 8) st_cluster_v4(map_to_rank(smem_u32(recv + (c.rank * 8 + m) * CL_NS + pc * 4), (uint32_t)peer), __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+                            else
+                            st_async_v4(map_to_rank(smem_u32(recv + (c.rank * 8 + m) * CL_NS + pc * 4), (uint32_t)peer),
+                                        __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w),
+                                        map_to_rank(bar, (uint32_t)peer));
+                        }
                     }
                     const float b2v = __ldg(W.b2 + c.rank * CL_NS + (c.tid & 63));
-                    ln_prefetch(c, W.ln3g, W.ln3b, lna);
-                    cl_sync(c);
+                    ln_prefetch(c, W.ln3g, W.ln3b);
+                    gather_wait(c);
+                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                     {
                         float* st2 = reinterpret_cast<float*>(c.smem + SM_RED);    // [8][64] staging of my reduced columns
                         const int m = c.tid >> 6, cc = c.tid & 63, col = c.rank * CL_NS + cc;
@@ -712,8 +767,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         consumer_bar();
                         push_f32_all(c, st2, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
                     }
-                    cl_sync(c);
-                    cl_layernorm(c, lna);
+                    gather_wait(c);
+                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
+                    cl_layernorm(c);
                     stamp(t, 10 + 8 * l);
                 }
                 // ================= [mel | stop] heads: ranks 0..5 own 16 of the 81(+15) columns =================
@@ -727,19 +783,26 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                                     p.stop_logits[(size_t)b * p.Tmax + t] = v;
                                     if (v > 0.f && p.finished[b] == 0) {                         // P10
                                         p.finished[b] = 1; p.lens[b] = t + 1; atomicAdd(p.n_finished, 1);
-                                        const uint32_t fa = smem_u32(const_cast<int*>(flags));
-#pragma unroll
-                                        for (int r = 0; r < CL_SIZE; ++r) red_cluster_add_u32(map_to_rank(fa, r), 1u);
+                                        atomicAdd(const_cast<int*>(flags), 1);                   // rank 5 keeps the group's count
                                     }
                                 }
                                 stg[m * 16 + n] = v;
                             });
                     if (c.rank < 5) push_bf16_all(c, stg, 16, fbuf + c.rank * 16, LDX128, 16);   // the frame = next step's prenet input
                 }
-                cl_sync(c);
+                if (c.tid < CL_SIZE) {                    // every rank contributes one record (rank 5: finished count) to every peer
+                    const uint32_t bar = gather_bar(c);
+                    if (c.dbg == 8) st_cluster_v4(map_to_rank(smem_u32(const_cast<int*>(hrec) + c.rank * 4), (uint32_t)c.tid), (uint32_t)flags[0], 0u, 0u, 0u);
+                    else
+                    st_async_v4(map_to_rank(smem_u32(const_cast<int*>(hrec) + c.rank * 4), (uint32_t)c.tid),
+                                (uint32_t)flags[0], 0u, 0u, 0u, map_to_rank(bar, (uint32_t)c.tid));
+                }
+                gather_wait(c);
+                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                 stamp(t, 51);
-                if (flags[0] >= c.G) break;                                   // every utterance of the group has fired
+                if (hrec[5 * 4] >= c.G) break;                               // every utterance of the group has fired
             }
+            group_done:
             // ---- tell the producer we are done; peers finish the group before anyone re-initialises buffers
             consumer_bar();
             if (c.tid == 0) { flags[2] = (int)c.consumed; __threadfence_block(); flags[1] = 1; }

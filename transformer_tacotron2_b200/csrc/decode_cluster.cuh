@@ -448,13 +448,13 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, floa
     uint32_t qb0[4] = {0, 0, 0, 0}, qb1[4] = {0, 0, 0, 0};
     if (active) {
         if (!self) vlen = min(L, __ldg(p.plens + c.b0 + gi));
-        if (g == 0) {                                    // B fragments of q (column 0 only), k slots <-> dims 16 t4 + 4 ks + {0..3}
+        // B fragments of q, replicated in all 8 columns (every lane then holds valid scores: the row max needs only
+        // 3 shuffles); k slots <-> dims 16 t4 + 4 ks + {0..3}
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const float* qp = qkv + gi * 192 + 16 * t4 + 4 * ks;
-                qb0[ks] = pack_bf16x2(qp[0] * qs, qp[1] * qs);
-                qb1[ks] = pack_bf16x2(qp[2] * qs, qp[3] * qs);
-            }
+        for (int ks = 0; ks < 4; ++ks) {
+            const float* qp = qkv + gi * 192 + 16 * t4 + 4 * ks;
+            qb0[ks] = pack_bf16x2(qp[0] * qs, qp[1] * qs);
+            qb1[ks] = pack_bf16x2(qp[2] * qs, qp[3] * qs);
         }
     }
     float m = -INFINITY, l = 0.f, o[4][4];
@@ -491,21 +491,29 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, floa
                 mma_bf16_16816(sc, a, qb0[ks], qb1[ks]);
             }
             const int r0 = ci * CL_KV_ROWS + g;
-            const float s0 = (t4 == 0 && r0 < vlen) ? sc[0] : -INFINITY;
-            const float s8 = (t4 == 0 && r0 + 8 < vlen) ? sc[2] : -INFINITY;
-            const float mnew = fmaxf(m, warp_max(fmaxf(s0, s8)));
+            const float s0 = r0 < vlen ? sc[0] : -INFINITY;
+            const float s8 = r0 + 8 < vlen ? sc[2] : -INFINITY;
+            float mx = fmaxf(s0, s8);                    // all columns are equal: reduce over the 8 row-groups only
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+            const float mnew = fmaxf(m, mx);
             if (mnew > -INFINITY) {                      // warp-uniform
-                const float scale = (m == -INFINITY) ? 0.f : exp2f(m - mnew);
-                const float p0 = exp2f(s0 - mnew), p8 = exp2f(s8 - mnew);
-                l = l * scale + p0 + p8;                 // lane-partial sum, reduced once at the end
+                const float p0 = fast_exp2(s0 - mnew), p8 = fast_exp2(s8 - mnew);
                 if (t4 == 0) { pscr[g] = p0; pscr[g + 8] = p8; }
+                if (mnew != m) {                         // warp-uniform: rescale only when the running max moved
+                    const float scale = (m == -INFINITY) ? 0.f : fast_exp2(m - mnew);
+                    l *= scale;
+#pragma unroll
+                    for (int dt = 0; dt < 4; ++dt) { o[dt][0] *= scale; o[dt][1] *= scale; o[dt][2] *= scale; o[dt][3] *= scale; }
+                }
+                l += (t4 == 0) ? p0 + p8 : 0.f;          // lane-partial sum, reduced once at the end
                 __syncwarp();
                 const float4 pv = *reinterpret_cast<const float4*>(pscr + 4 * t4);
                 __syncwarp();
-                const uint32_t b0 = g == 0 ? pack_bf16x2(pv.x, pv.y) : 0u, b1 = g == 0 ? pack_bf16x2(pv.z, pv.w) : 0u;
+                const uint32_t b0 = pack_bf16x2(pv.x, pv.y), b1 = pack_bf16x2(pv.z, pv.w);     // p replicated in all columns too
 #pragma unroll
                 for (int dt = 0; dt < 4; ++dt) {
-                    o[dt][0] *= scale; o[dt][1] *= scale; o[dt][2] *= scale; o[dt][3] *= scale;
                     const uint32_t a[4] = {vf[dt][0].x, vf[dt][1].x, vf[dt][0].y, vf[dt][1].y};
                     mma_bf16_16816(o[dt], a, b0, b1);
                 }
@@ -520,7 +528,7 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, floa
             const float2 kd = unpack_bf16x2(pack_bf16x2(qp[64], qp[65]));
             const float st = warp_sum(qd.x * kd.x + qd.y * kd.y);
             const float mnew = fmaxf(m, st);
-            const float scale = (m == -INFINITY) ? 0.f : exp2f(m - mnew), pt = exp2f(st - mnew);
+            const float scale = (m == -INFINITY) ? 0.f : fast_exp2(m - mnew), pt = fast_exp2(st - mnew);
             l = l * scale + (c.lane == 0 ? pt : 0.f);
 #pragma unroll
             for (int dt = 0; dt < 4; ++dt) {
@@ -544,7 +552,7 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, floa
         const float* pa = pscr;
         const float* pb = pscr + 68;
         const float ma = pa[64], mb = pb[64], mm = fmaxf(ma, mb);
-        const float ea = (ma == -INFINITY) ? 0.f : exp2f(ma - mm), eb = (mb == -INFINITY) ? 0.f : exp2f(mb - mm);
+        const float ea = (ma == -INFINITY) ? 0.f : fast_exp2(ma - mm), eb = (mb == -INFINITY) ? 0.f : fast_exp2(mb - mm);
         const float ls = pa[65] * ea + pb[65] * eb;
         const float inv = ls > 0.f ? 1.f / ls : 0.f;
         stage[gi * 64 + c.lane] = (pa[c.lane] * ea + pb[c.lane] * eb) * inv;

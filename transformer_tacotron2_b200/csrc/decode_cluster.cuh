@@ -99,6 +99,9 @@ TTS_D void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c2, uin
 TTS_D void red_cluster_add_u32(uint32_t addr, uint32_t v) { asm volatile("red.shared::cluster.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 TTS_D void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
 TTS_D void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+TTS_D void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
 TTS_D void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -153,6 +156,18 @@ TTS_D int seg_chunks(int seg, int t, int S, int G, int rank, int dbg = 0) {
     case 1: return (t + CL_KV_ROWS - 1) / CL_KV_ROWS;
     case 4: return (S + CL_KV_ROWS - 1) / CL_KV_ROWS;
     default: return 2;
+    }
+}
+// consumer warps that read a chunk of segment `seg` (the producer arrives on the slot's empty barrier for the others,
+// so warps that do not need a chunk never touch it and a slot is free again as soon as its readers have loaded it)
+TTS_D int seg_readers(int seg, int G) {
+    if (seg == 0) return 4;
+    if (seg == 1 || seg == 51) return 8;
+    if (seg == 2) return 16;
+    switch ((seg - 3) & 7) {
+    case 0: return 12;
+    case 1: case 4: return G;                      // one warp per (utterance, head) pair and chunk
+    default: return 16;
     }
 }
 TTS_D uint32_t seg_weight_bytes(int seg) {          // bytes per chunk of a weight segment
@@ -213,6 +228,10 @@ TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* fu
                     bulk_g2s(dst, wbase + woff, bytes, &full[stage], pol_w);
                 }
                 if (!(sub == 1 || sub == 4)) woff += seg_weight_bytes(seg);
+                {
+                    const int nskip = CL_WARPS - seg_readers(seg, G);
+                    if (lane == 0 && nskip > 0) mbar_arrive_n(&empty[stage], (uint32_t)nskip);
+                }
                 ++issued;
             }
         }
@@ -276,9 +295,11 @@ TTS_D void cl_gemm(ClCtx& c, int nchunks, int NT, int KSPLIT, bool typeB, const 
         }
     }
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!active) c.consumed += nchunks;                  // the producer released these chunks on my behalf
+    else
     for (int ch = 0; ch < nchunks; ++ch) {
         const unsigned char* st = cl_acquire(c);
-        if (active) {
+        {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int bi = c.warp * 2 + j;
@@ -461,11 +482,12 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, floa
 #pragma unroll
     for (int i = 0; i < 4; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
     for (int ci = 0; ci < nck; ++ci) {
+        const bool mine = active && (ci & 1) == par2;
+        if (!mine) { ++c.consumed; continue; }           // not my chunk: the producer / its owner release it
         const unsigned char* st = cl_acquire(c);
         uint32_t kr[8], kr8[8];
         uint2 vf[4][2];
-        const bool mine = active && (ci & 1) == par2;
-        if (mine) {
+        {
             const unsigned char* kb = st + gi * 2048;
             const unsigned char* vb = st + 16384 + gi * 2048;
             const int par = g & 1;                       // XOR-ordered 16-byte loads: conflict-free at a 128 B row stride

@@ -279,7 +279,7 @@ def run_b200(args, rank, world, local_rank):
                    "weights": "random-init (seed 1234), stop head planted so no utterance stops early"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "decode_kernel (persistent, all decoder steps of one batch in one launch)",
+        "roofline": {"bound": "hbm", "kernel": "decode_cluster_kernel (persistent 8-CTA clusters, all decoder steps of one batch in one launch)",
                      "achieved": achieved, "peak": peak, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo,
                      "kernel_ms_per_launch": dec_ms, "us_per_decoder_step": 1e3 * dec_ms / T},

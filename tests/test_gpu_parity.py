@@ -186,3 +186,40 @@ def test_repeatable(models):
     assert torch.equal(a1, a2) and torch.equal(s1, s2)
     a3, _, _ = g.inference(ph, pl, max_len=12, seed=10)
     assert not torch.equal(a1, a3)                      # the dropout seed matters (P7)
+
+
+def test_long_utterance_shapes_vs_oracle(models):
+    """configs[4]-like geometry at a size the oracle finishes in seconds: 300 phonemes (19 cross-K/V chunks, ragged),
+    several hundred frames (free-running drift over many steps stays inside the tolerance)."""
+    from oracle import synthetic
+    o, g, _, _ = models
+    ph, pl, _, _ = synthetic.make_inputs(2, 300, 8, 81, ragged=True)
+    ma, lens, st = o.inference(ph, pl, max_len=260, seed=7)
+    ga, gl, gs = (t.cpu() for t in g.inference(ph.cuda(), pl.cuda(), max_len=260, seed=7))
+    print(f"S=300 T=260: rel-L2 {rel_l2(ga, ma):.4f} stop err {float((gs - st).abs().max()):.4f}")
+    assert gl.tolist() == lens.tolist()
+    assert rel_l2(ga, ma) < TOL_AR and float((gs - st).abs().max()) < TOL_STOP
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[2] at full size (B = 64, S = 100, 800 frames), where the oracle would take minutes:
+    size-independent properties -- every utterance decodes all frames (planted stop head), outputs are finite,
+    two runs are bit-identical, and a shard with global utterance ids reproduces its slice bit for bit."""
+    from bench import synthetic_state_dict, synthetic_inputs
+    from transformer_tacotron2_b200 import TransformerTTS
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    m = TransformerTTS(); m.load_state_dict(synthetic_state_dict().state_dict())
+    ph, pl = synthetic_inputs(64, 100, 103)
+    a1, l1, s1 = m.inference(ph.cuda(), pl.cuda(), max_len=800, seed=7)
+    assert a1.shape == (64, 800, 80) and l1.tolist() == [800] * 64
+    assert bool(torch.isfinite(a1).all()) and bool(torch.isfinite(s1).all()) and float(s1.max()) < 0
+    a2, l2, s2 = m.inference(ph.cuda(), pl.cuda(), max_len=800, seed=7)
+    assert torch.equal(a1, a2) and torch.equal(s1, s2)
+    a3, l3, s3 = m.inference(ph[24:40].cuda(), pl[24:40].cuda(), max_len=800, seed=7, utt_offset=24)
+    assert torch.equal(a3, a1[24:40]) and torch.equal(s3, s1[24:40])
+    # mean / spread of the generated frames are those of the same model run through the teacher-forced path
+    # on its own output (KV-cache decode == full-sequence recompute, up to bf16 rounding)
+    mb = m.inference(ph[:4].cuda(), pl[:4].cuda(), max_len=800, seed=7, return_before=True)[3]
+    tb, ta, ts = m(ph[:4], pl[:4], mb.cpu(), torch.full((4,), 800, dtype=torch.int32), seed=7)
+    assert rel_l2(ta, a1[:4]) < 3e-2

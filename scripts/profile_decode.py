@@ -58,12 +58,3 @@ if os.environ.get("TTS_GROUPS"):
             m.inference(ph, pl, max_len=T, seed=7)
         print(f"cluster_group={G}: decode {min(m.decode_ms):.2f} ms -> {1e3*min(m.decode_ms)/T:.1f} us/step")
 
-if os.environ.get("TTS_DBG_MODES"):
-    m.set_option("cluster_group", 0); m.set_option("decode_timestamps", 0)
-    for mode in [int(x) for x in os.environ["TTS_DBG_MODES"].split(",")]:
-        m.set_option("debug_mode", mode)
-        m.profile_events = True; m.decode_ms.clear()
-        for _ in range(2):
-            m.inference(ph, pl, max_len=T, seed=7)
-        print(f"debug_mode={mode}: decode {min(m.decode_ms):.2f} ms -> {1e3*min(m.decode_ms)/T:.1f} us/step")
-    m.set_option("debug_mode", 0)

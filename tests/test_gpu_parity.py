@@ -113,10 +113,10 @@ def test_inference_stopping_vs_oracle_and_golden(models):
     assert rel_l2(ga, torch.from_numpy(z["mel_after"])) < TOL_AR
 
 
-@pytest.mark.parametrize("B,S,T,G", [(1, 10, 20, 0), (5, 33, 40, 0), (8, 20, 150, 8), (11, 24, 30, 4), (20, 50, 64, 3), (9, 100, 33, 8)])
+@pytest.mark.parametrize("B,S,T,G", [(1, 10, 20, 0), (5, 33, 40, 0), (8, 20, 150, 5), (11, 24, 30, 4), (20, 50, 64, 3), (9, 100, 33, 5), (90, 12, 18, 0)])
 def test_cluster_kernel_vs_oracle(models, B, S, T, G):
     """The cluster-partitioned decode kernel against the oracle across group shapes: partial groups, full
-    groups of 8, several clusters, ragged phoneme lengths, frame counts that are / are not multiples of the
+    groups of 5, several clusters, more groups than co-resident clusters, ragged phoneme lengths, frame counts that are / are not multiples of the
     16-row K/V chunk, and explicit utterances-per-cluster settings."""
     from oracle import synthetic
     o, _, _, _ = models
@@ -135,7 +135,7 @@ def test_group_size_does_not_change_results(models):
     o, _, _, _ = models
     ph, pl, _, _ = synthetic.make_inputs(10, 30, 8, 71, ragged=True)
     outs = []
-    for G in (8, 5, 2):
+    for G in (5, 3, 2):
         g = make_b200_model(o, cluster_group=G)
         outs.append([t.cpu() for t in g.inference(ph.cuda(), pl.cuda(), max_len=37, seed=7)])
     for a, l, s_ in outs[1:]:

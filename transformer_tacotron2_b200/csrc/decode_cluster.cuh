@@ -29,8 +29,11 @@
 
 namespace tts {
 
-constexpr int CL_SIZE = 8, CL_CONSUMERS = 512, CL_THREADS = 544, CL_WARPS = 16, CL_G = 8;
-constexpr int CL_STAGES = 4, CL_STAGE_BYTES = 32768, CL_KV_ROWS = 16;   // K/V chunk: 16 rows of every pair of the CTA
+constexpr int CL_SIZE = 8, CL_CONSUMERS = 512, CL_THREADS = 544, CL_WARPS = 16;
+// Row capacity of a cluster.  5 rather than the MMA's 8: the activation buffers shrink by 35 KB, which buys a fifth
+// 32 KB ring stage (128 KB instead of 96 KB in flight per SM); B = 64 still fits one pass (13 clusters of <= 15).
+constexpr int CL_G = 5;
+constexpr int CL_STAGES = 5, CL_STAGE_BYTES = 32768, CL_KV_ROWS = 16;   // K/V chunk: 16 rows of every pair of the CTA
 constexpr int CL_NS = 512 / CL_SIZE;                 // 64: columns of a 512-wide output owned by one rank
 
 // bytes of one rank's packed weight segments (stream order: fc1 fc2 proj | 6 x (qkv o q2 o2 w1 w2) | head)
@@ -41,20 +44,23 @@ constexpr size_t CLW_RANK_BYTES = (size_t)CLW_FC1 + CLW_FC2 + CLW_PROJ + 6 * (si
 
 // shared memory carve-up (bytes)
 constexpr int SM_RING = 0;
-constexpr int SM_XRES = SM_RING + CL_STAGES * CL_STAGE_BYTES;   // f32 [8][512]  residual stream
-constexpr int SM_YBUF = SM_XRES + 16384;                        // f32 [8][512]  gathered pre-LN sums / FFN2 partial staging
-constexpr int SM_RECV = SM_YBUF + 16384;                        // f32 [8 ranks][8][64] FFN2 reduce-scatter; epilogue staging otherwise
-constexpr int SM_RED = SM_RECV + 16384;                         // f32 [16][128] K-split partials
-constexpr int SM_XA = SM_RED + 8192;                            // bf16 [8][520] LN output as MMA operand
-constexpr int SM_ABUF = SM_XA + 8320;                           // bf16 [8][520] gathered attention outputs
-constexpr int SM_QKV = SM_ABUF + 8320;                          // f32 [8][192]  q | k_t | v_t of this head
-constexpr int SM_HBUF = SM_QKV + 6144;                          // bf16 [8][264] FFN hidden slice (local)
-constexpr int SM_H1 = SM_HBUF + 4224;                           // bf16 [8][264] gathered prenet activations
-constexpr int SM_H2 = SM_H1 + 4224;
-constexpr int SM_FBUF = SM_H2 + 4224;                           // bf16 [8][136] previous frame (K padded to 128)
-constexpr int SM_AMERGE = SM_FBUF + 2176;                       // f32 [16][68]  attention warp partials
-constexpr int SM_MISC = SM_AMERGE + 4352;                       // mbarriers + flags
-constexpr int CL_SMEM_BYTES = SM_MISC + 320;             // barriers (128) + flags (32) + 8 head records (128)
+constexpr int SM_XRES = SM_RING + CL_STAGES * CL_STAGE_BYTES;   // f32 [G][512]  residual stream
+constexpr int SM_YBUF = SM_XRES + CL_G * 2048;                  // f32 [G][512]  gathered pre-LN sums / FFN2 partial staging
+constexpr int SM_RECV = SM_YBUF + CL_G * 2048;                  // f32 [8 ranks][G][64] FFN2 reduce-scatter; epilogue staging otherwise
+constexpr int SM_RED = SM_RECV + CL_G * 2048;                   // f32 [16][128] K-split partials; [4096, 8192): LayerNorm gamma | beta
+constexpr int SM_XA = SM_RED + 8192;                            // bf16 [G][520] LN output as MMA operand
+constexpr int SM_ABUF = SM_XA + CL_G * 1040;                    // bf16 [G][520] gathered attention outputs (prenet: h2 [G][264])
+constexpr int SM_QKV = SM_ABUF + CL_G * 1040;                   // f32 [G][192]  q | k_t | v_t of this head
+constexpr int SM_HBUF = SM_QKV + CL_G * 768;                    // bf16 [G][264] FFN hidden slice (local)
+constexpr int SM_H1 = SM_HBUF + CL_G * 528;                     // bf16 [G][264] gathered prenet activations
+constexpr int SM_H2 = SM_ABUF;                                  // aliases abuf (idle during the prenet)
+constexpr int SM_FBUF = SM_H1 + CL_G * 528;                     // bf16 [G][136] previous frame (K padded to 128)
+constexpr int SM_AMERGE = SM_FBUF + CL_G * 272;                 // f32 [16][68]  attention warp scratch
+constexpr int SM_MISC = SM_AMERGE + 4352;                       // mbarriers + flags + head records
+constexpr int CL_SMEM_BYTES = SM_MISC + 320;
+static_assert(CL_SMEM_BYTES <= 232448, "decode kernel shared memory exceeds 227 KB");
+// (MMA B fragments are loaded with ldmatrix over 8 rows: rows >= G read whatever follows the buffer -- finite or not, they
+//  only feed output columns m >= G, which are never used.)
 constexpr int LDX512 = 520, LDX256 = 264, LDX128 = 136;
 
 struct ClusterLayerParams {
@@ -76,7 +82,6 @@ struct ClusterParams {
     const int* plens;
     float* mel_before; float* stop_logits; int* lens; int* finished; int* n_finished;
     unsigned long long* ts;                      // optional [Tmax][64] %globaltimer stamps (cluster 0, rank 0)
-    int dbg;                                     // profiling experiments (results invalid): 1 skip attention math, 2 contiguous K/V copies
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -139,16 +144,11 @@ struct ClCtx {
     uint32_t consumed;                   // chunks consumed (uniform over the consumer warps)
     uint32_t sync_phase;                 // cluster barrier phase counter
     uint32_t gphase;                     // gather phase counter (40 per decoder step)
-    int dbg;
 };
 
 // The ordered stream of chunks of one step for one rank.  seg: 0 fc1, 1 fc2, 2 proj,
 // 3+8l+{0 qkv, 1 self-KV, 2 o, 3 q2, 4 cross-KV, 5 o2, 6 w1, 7 w2}, 51 head.
-TTS_D int seg_chunks(int seg, int t, int S, int G, int rank, int dbg = 0) {
-    if (dbg == 6 || dbg == 7) {                          // profiling experiments: weights only / K,V only
-        const bool kv = seg >= 3 && seg < 51 && (((seg - 3) & 7) == 1 || ((seg - 3) & 7) == 4);
-        if ((dbg == 6 && kv) || (dbg == 7 && !kv)) return 0;
-    }
+TTS_D int seg_chunks(int seg, int t, int S, int G, int rank) {
     if (seg < 3) return 1;
     if (seg == 51) return rank < 6 ? 1 : 0;
     switch ((seg - 3) & 7) {
@@ -192,7 +192,7 @@ TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* fu
     for (int t = t0; t < t_end && !stopped; ++t) {
         size_t woff = 0;
         for (int seg = 0; seg <= 51 && !stopped; ++seg) {
-            const int n = seg_chunks(seg, t, p.S, G, rank, p.dbg);
+            const int n = seg_chunks(seg, t, p.S, G, rank);
             const int sub = (seg < 3 || seg == 51) ? -1 : ((seg - 3) & 7);
             for (int i = 0; i < n; ++i) {
                 const int stage = issued % CL_STAGES;
@@ -211,16 +211,8 @@ TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* fu
                         const int l = (seg - 3) >> 3;
                         const CUtensorMap* tm = sub == 1 ? &p.tm_self : &p.tm_cross;
                         mbar_expect_tx(&full[stage], 2u * (uint32_t)p.G * 2048u);
-                        if (p.dbg == 2) {
-                            const bf16* base = sub == 1 ? p.self_kv : p.cross_kv;
-                            const int Lp = sub == 1 ? p.Tpad : p.Spad;
-                            const size_t idx = ((((size_t)(l * 2) * p.B + b0) * kHeads + rank) * Lp + (size_t)(i % 8) * p.G * CL_KV_ROWS) * kDHead;
-                            bulk_g2s(dst, base + idx, (uint32_t)p.G * 2048u, &full[stage], pol_kv);
-                            bulk_g2s(dst + 16384, base + idx + (size_t)p.B * kHeads * Lp * kDHead, (uint32_t)p.G * 2048u, &full[stage], pol_kv);
-                        } else {
                         tma_g2s_4d(dst, tm, 0, i * CL_KV_ROWS, rank, (l * 2) * p.B + b0, &full[stage], pol_kv);
                         tma_g2s_4d(dst + 16384, tm, 0, i * CL_KV_ROWS, rank, (l * 2 + 1) * p.B + b0, &full[stage], pol_kv);
-                        }
                     }
                 } else if (lane == 0) {
                     const uint32_t bytes = seg_weight_bytes(seg);
@@ -261,7 +253,6 @@ TTS_D void cl_release(ClCtx& c) {
 // cluster-wide barrier of the consumer warps: my DSMEM pushes are visible to every peer afterwards
 TTS_D void cl_sync(ClCtx& c) {
     consumer_bar();
-    if (c.dbg == 3) return;                              // profiling experiment: no cluster barrier (results invalid)
     if (c.tid < CL_SIZE) mbar_arrive_remote(map_to_rank(smem_u32(c.csync), (uint32_t)c.tid));
     while (!mbar_try_wait_cluster(c.csync, c.sync_phase & 1)) {}
     ++c.sync_phase;
@@ -368,11 +359,9 @@ TTS_D uint32_t gather_bytes(int ph, int G) {
     return (k == 0 || k == 2) ? 1024u * G : 2048u * G;   // attention outputs (bf16) : f32 slices (O, O2, reduce-scatter, y3)
 }
 TTS_D uint32_t gather_bar(const ClCtx& c) { return smem_u32(&c.gsync[c.gphase & 1]); }
-TTS_D void cl_sync(ClCtx& c);
 TTS_D void gather_wait(ClCtx& c) {
-    if (c.dbg == 8) { cl_sync(c); ++c.gphase; return; }   // experiment: classic push + arrive/wait barrier
     uint64_t* bar = &c.gsync[c.gphase & 1];
-    if (c.dbg != 3) mbar_wait(bar, (c.gphase >> 1) & 1);
+    mbar_wait(bar, (c.gphase >> 1) & 1);
     if (c.tid == 0) mbar_expect_tx(bar, gather_bytes((int)((c.gphase + 2) % 40), c.G));
     ++c.gphase;
 }
@@ -383,8 +372,6 @@ TTS_D void push_f32_all(const ClCtx& c, const float* stage, int ld, float* dst, 
     for (int i = c.tid; i < per_peer * CL_SIZE; i += CL_CONSUMERS) {
         const int peer = i / per_peer, j = i % per_peer, m = j / ppr, pc = j - m * ppr;
         const float4 v = *reinterpret_cast<const float4*>(stage + m * ld + pc * 4);
-        if (c.dbg == 8) st_cluster_v4(map_to_rank(smem_u32(dst + m * dld + pc * 4), (uint32_t)peer), __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
-        else
         st_async_v4(map_to_rank(smem_u32(dst + m * dld + pc * 4), (uint32_t)peer),
                     __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w), map_to_rank(bar, (uint32_t)peer));
     }
@@ -397,8 +384,6 @@ TTS_D void push_bf16_all(const ClCtx& c, const float* stage, int ld, bf16* dst, 
         const int peer = i / per_peer, j = i % per_peer, m = j / ppr, pc = j - m * ppr;
         const float4 v0 = *reinterpret_cast<const float4*>(stage + m * ld + pc * 8);
         const float4 v1 = *reinterpret_cast<const float4*>(stage + m * ld + pc * 8 + 4);
-        if (c.dbg == 8) st_cluster_v4(map_to_rank(smem_u32(dst + m * dld + pc * 8), (uint32_t)peer), pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
-        else
         st_async_v4(map_to_rank(smem_u32(dst + m * dld + pc * 8), (uint32_t)peer),
                     pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w), map_to_rank(bar, (uint32_t)peer));
     }
@@ -406,9 +391,9 @@ TTS_D void push_bf16_all(const ClCtx& c, const float* stage, int ld, bf16* dst, 
 
 // LayerNorm of the gathered rows: ybuf -> xres (f32) + xa (bf16); warp m < G owns row m.  The affine parameters
 // (global memory) are fetched asynchronously into shared memory by ln_prefetch() BEFORE the exchange the rows are
-// waited on (buffer: the prenet's h1 region, idle while the layers run).
+// waited on (buffer: the upper half of the K-split scratch, idle between GEMMs).
 TTS_D void ln_prefetch(const ClCtx& c, const float* g, const float* b) {
-    float* dst = reinterpret_cast<float*>(c.smem + SM_H1);               // [0,512) gamma, [512,1024) beta
+    float* dst = reinterpret_cast<float*>(c.smem + SM_RED + 4096);        // [0,512) gamma, [512,1024) beta
     if (c.tid < 256) {
         const float* src = (c.tid < 128 ? g : b) + (c.tid & 127) * 4;
         cp_async_16(dst + c.tid * 4, src, true);
@@ -418,9 +403,9 @@ TTS_D void ln_prefetch(const ClCtx& c, const float* g, const float* b) {
 TTS_D void cl_layernorm(ClCtx& c) {
     cp_async_wait<0>();
     consumer_bar();
-    if (c.warp < c.G && c.dbg != 4) {
+    if (c.warp < c.G) {
         const float* y = reinterpret_cast<const float*>(c.smem + SM_YBUF) + c.warp * 512;
-        const float* gb = reinterpret_cast<const float*>(c.smem + SM_H1);
+        const float* gb = reinterpret_cast<const float*>(c.smem + SM_RED + 4096);
         float* xr = reinterpret_cast<float*>(c.smem + SM_XRES) + c.warp * 512;
         bf16* xa = reinterpret_cast<bf16*>(c.smem + SM_XA) + c.warp * LDX512;
         float v[16];
@@ -505,7 +490,7 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, floa
             }
         }
         cl_release(c);
-        if (mine && p.dbg != 1) {
+        {
             float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
@@ -599,7 +584,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
     volatile int* hrec = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 128 + 32);     // [8 ranks][4]
     c.rank = (int)cluster_ctarank();
     c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
-    c.sync_phase = 0; c.dbg = p.dbg;
+    c.sync_phase = 0;
     const int cid = (int)cluster_id_x(), ncl = (int)cluster_nid_x();
     const bool is_producer = c.warp == CL_WARPS;
 
@@ -660,14 +645,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
         } else if (skip) {
             cl_sync(c); cl_sync(c);
         } else {
-            { const int d = c.dbg; c.dbg = 0; cl_sync(c); c.dbg = d; }   // peers' buffers are initialised before any DSMEM push
-            if (c.dbg >= 5) {                            // profiling experiment: drain the chunk stream, no compute (results invalid)
-                for (int t = t0; t < t0 + n_steps; ++t)
-                    for (int seg = 0; seg <= 51; ++seg) {
-                        const int n = seg_chunks(seg, t, p.S, c.G, c.rank, c.dbg);
-                        for (int i = 0; i < n; ++i) { cl_acquire(c); cl_release(c); }
-                    }
-            } else
+            cl_sync(c);                                  // peers' buffers are initialised before any DSMEM push
             for (int t = t0; t < t0 + n_steps; ++t) {
                 // ================= decoder prenet (dropout always on, P7) =================
                 cl_gemm(c, 1, 2, 2, false, fbuf, LDX128,
@@ -679,7 +657,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         });
                 push_bf16_all(c, stg, 32, h1 + c.rank * 32, LDX256, 32);
                 gather_wait(c);
-                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                 stamp(t, 0);
                 cl_gemm(c, 1, 2, 4, false, h1, LDX256,
                         [&](int ti, int n) { return __ldg(p.b_fc2 + c.rank * 32 + ti * 16 + n); },
@@ -690,7 +667,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         });
                 push_bf16_all(c, stg, 32, h2 + c.rank * 32, LDX256, 32);
                 gather_wait(c);
-                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                 stamp(t, 1);
                 cl_gemm(c, 1, 4, 4, false, h2, LDX256,
                         [&](int ti, int n) {
@@ -701,7 +677,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                 push_f32_all(c, stg, CL_NS, xres + c.rank * CL_NS, 512, CL_NS);
                 push_bf16_all(c, stg, CL_NS, xa + c.rank * CL_NS, LDX512, CL_NS);
                 gather_wait(c);
-                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                 stamp(t, 2);
 
                 for (int l = 0; l < 6; ++l) {
@@ -725,7 +700,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     stamp(t, 3 + 8 * l);
                     cl_attention(p, c, true, t, stg);
                     gather_wait(c);
-                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                     stamp(t, 4 + 8 * l);
                     // ---- O projection + residual, gathered -> LayerNorm 1
                     cl_gemm(c, 2, 4, 4, false, abuf, LDX512,
@@ -737,7 +711,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     ln_prefetch(c, W.ln1g, W.ln1b);
                     push_f32_all(c, stg, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
                     gather_wait(c);
-                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                     cl_layernorm(c);
                     stamp(t, 5 + 8 * l);
                     // ---- cross-attention query of head `rank` (local)
@@ -747,7 +720,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     stamp(t, 6 + 8 * l);
                     cl_attention(p, c, false, t, stg);
                     gather_wait(c);
-                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                     stamp(t, 7 + 8 * l);
                     cl_gemm(c, 2, 4, 4, false, abuf, LDX512,
                             [&](int ti, int n) { return __ldg(W.bo2 + c.rank * CL_NS + ti * 16 + n); },
@@ -758,7 +730,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     ln_prefetch(c, W.ln2g, W.ln2b);
                     push_f32_all(c, stg, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
                     gather_wait(c);
-                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                     cl_layernorm(c);
                     stamp(t, 8 + 8 * l);
                     // ---- FFN: hidden slice [256 rank, +256) stays local (bf16); FFN2 is split along K
@@ -774,9 +745,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         for (int i = c.tid; i < CL_SIZE * c.G * 16; i += CL_CONSUMERS) {   // reduce-scatter: 64 columns to each peer
                             const int peer = i / (c.G * 16), j = i % (c.G * 16), m = j >> 4, pc = j & 15;
                             const float4 v = *reinterpret_cast<const float4*>(ybuf + m * 512 + peer * CL_NS + pc * 4);
-                            if (c.dbg == 8) st_cluster_v4(map_to_rank(smem_u32(recv + (c.rank * 8 + m) * CL_NS + pc * 4), (uint32_t)peer), __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
-                            else
-                            st_async_v4(map_to_rank(smem_u32(recv + (c.rank * 8 + m) * CL_NS + pc * 4), (uint32_t)peer),
+                            st_async_v4(map_to_rank(smem_u32(recv + (c.rank * CL_G + m) * CL_NS + pc * 4), (uint32_t)peer),
                                         __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w),
                                         map_to_rank(bar, (uint32_t)peer));
                         }
@@ -784,21 +753,19 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     const float b2v = __ldg(W.b2 + c.rank * CL_NS + (c.tid & 63));
                     ln_prefetch(c, W.ln3g, W.ln3b);
                     gather_wait(c);
-                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                     {
                         float* st2 = reinterpret_cast<float*>(c.smem + SM_RED);    // [8][64] staging of my reduced columns
                         const int m = c.tid >> 6, cc = c.tid & 63, col = c.rank * CL_NS + cc;
                         if (m < c.G) {
                             float v = b2v + xres[m * 512 + col];
 #pragma unroll
-                            for (int r = 0; r < CL_SIZE; ++r) v += recv[(r * 8 + m) * CL_NS + cc];    // fixed order
+                            for (int r = 0; r < CL_SIZE; ++r) v += recv[(r * CL_G + m) * CL_NS + cc];    // fixed order
                             st2[m * CL_NS + cc] = v;
                         }
                         consumer_bar();
                         push_f32_all(c, st2, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
                     }
                     gather_wait(c);
-                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                     cl_layernorm(c);
                     stamp(t, 10 + 8 * l);
                 }
@@ -822,21 +789,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                 }
                 if (c.tid < CL_SIZE) {                    // every rank contributes one record (rank 5: finished count) to every peer
                     const uint32_t bar = gather_bar(c);
-                    if (c.dbg == 8) st_cluster_v4(map_to_rank(smem_u32(const_cast<int*>(hrec) + c.rank * 4), (uint32_t)c.tid), (uint32_t)flags[0], 0u, 0u, 0u);
-                    else
                     st_async_v4(map_to_rank(smem_u32(const_cast<int*>(hrec) + c.rank * 4), (uint32_t)c.tid),
                                 (uint32_t)flags[0], 0u, 0u, 0u, map_to_rank(bar, (uint32_t)c.tid));
                 }
                 gather_wait(c);
-                if (c.dbg >= 100 && (int)c.gphase >= c.dbg - 100) goto group_done;
                 stamp(t, 51);
                 if (hrec[5 * 4] >= c.G) break;                               // every utterance of the group has fired
             }
-            group_done:
             // ---- tell the producer we are done; peers finish the group before anyone re-initialises buffers
             consumer_bar();
             if (c.tid == 0) { flags[2] = (int)c.consumed; __threadfence_block(); flags[1] = 1; }
-            { const int d = c.dbg; c.dbg = 0; cl_sync(c); c.dbg = d; }
+            cl_sync(c);
         }
         __syncthreads();                                 // producer has drained the ring
     }

@@ -29,7 +29,6 @@ struct TtsHandle {
     std::map<std::string, std::vector<float>> staged;
     bool finalized = false;
     int decode_timestamps = 0;
-    int dbg_mode = 0;
     int cluster_group = 0;                                            // utterances per cluster (1..8); 0 = auto
     int cluster_ok = -1, max_clusters = 0;                            // probed lazily
     unsigned char* cl_wpack = nullptr;                                // [16][CLW_RANK_BYTES] (own allocation)
@@ -139,8 +138,7 @@ extern "C" int tts_destroy(TtsHandle* h) {
 extern "C" int tts_set_option(TtsHandle* h, const char* key, int64_t value) {
     if (!h || !key) return TTS_E_ARG;
     if (!strcmp(key, "decode_timestamps")) { h->decode_timestamps = value ? 1 : 0; return 0; }
-    if (!strcmp(key, "debug_mode")) { h->dbg_mode = (int)value; return 0; }
-    if (!strcmp(key, "cluster_group")) { if (value < 0 || value > CL_G) FAIL(TTS_E_ARG, "cluster_group must be 0 (auto) or 1..8"); h->cluster_group = (int)value; return 0; }
+    if (!strcmp(key, "cluster_group")) { if (value < 0 || value > CL_G) FAIL(TTS_E_ARG, "cluster_group must be 0 (auto) or 1..5"); h->cluster_group = (int)value; return 0; }
     if (!strcmp(key, "print_info")) { fprintf(stderr, "[tts_b200] sms=%d cluster_ok=%d max_clusters=%d group=%d ngroups=%d\n", h->num_sms, h->cluster_ok, h->max_clusters, h->cparams.G, h->cparams.ngroups); return 0; }
     FAIL(TTS_E_ARG, std::string("unknown option ") + key);
 }
@@ -591,7 +589,6 @@ extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* strea
     at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     h->cparams.ts = h->decode_timestamps ? wsp<unsigned long long>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).ts) : nullptr;
-    h->cparams.dbg = h->dbg_mode;
     CK(cudaLaunchKernelEx(&cfg, decode_cluster_kernel, h->cparams, h->dec_t, n_steps));
     ++launch_counter();
     h->dec_t += n_steps;                                                // upper bound; tts_decode_status refines it

@@ -1,0 +1,276 @@
+// tcgen05 / TMEM / TMA GEMM for the sequence-parallel path (component C12):
+//     C[m, n] = epi( sum_tap sum_k A[b, t + tap - pad, k] * W[tap][n, k] ),   m = b * T + t
+// i.e. plain GEMMs (taps = 1, T = M) and conv1d(k = 5, pad = 2) as 5 row-shifted GEMMs accumulated into ONE
+// TMEM accumulator; rows outside [0, T) of their own utterance are zero-filled by TMA's out-of-bounds handling
+// (the A operand is a 3-D tensor map {channels, frames, utterances}), so no padded copies exist.
+// Structure (one 128 x 128 output tile per CTA, 192 threads):
+//   warp 0  : TMA producer      cp.async.bulk.tensor -> 4-stage shared-memory ring (128B swizzle), mbarrier full/empty
+//   warp 1  : MMA issuer        one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16), accumulator
+//                               in TMEM (128 fp32 columns); tcgen05.commit releases ring slots / signals the epilogue
+//   warps 2-5: epilogue         tcgen05.ld 32x32b (thread = output row) -> fused epilogue of gemm_mma.cuh (bias, BN fold,
+//                               ReLU / tanh, residual, alpha*PE, length mask, Philox dropout, KV scatter, head split)
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_mma.cuh"
+#include "philox.cuh"
+
+namespace tts {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 4;
+constexpr int TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2;              // 32 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256;   // + alignment slack + barriers
+constexpr int TC_THREADS = 192;
+
+struct GemmTcParams {
+    alignas(64) CUtensorMap tm_a;     // bf16 {K (inner), T, B}, box {64, 128, 1}, SWIZZLE_128B
+    alignas(64) CUtensorMap tm_w;     // bf16 {K (inner), taps * Nw}, box {64, 128}, SWIZZLE_128B
+    GemmParams g;                     // shapes + epilogue (A / W pointers unused here)
+    int Tl;                           // rows per A-tensor slab: T for convs (taps > 1), M for plain GEMMs
+    int tiles_per_utt;                // ceil(Tl / 128)
+};
+
+TTS_D uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+TTS_D void tc_mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count) : "memory"); }
+TTS_D void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+TTS_D void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+}
+TTS_D void tc_tma_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(tc_smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(tc_smem_u32(bar)) : "memory");
+}
+TTS_D void tc_tma_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(tc_smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(tc_smem_u32(bar)) : "memory");
+}
+// K-major operand tile [rows][64 bf16] written by TMA with 128-byte swizzle: 8-row atoms of 1024 B (SBO = 1024 B),
+// LBO unused (1), descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B)  -- cute::UMMA::SmemDescriptor
+TTS_D uint64_t tc_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9 = 1, 10-12 = 1), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28  -- cute::UMMA::InstrDescriptor
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty = full + TC_STAGES;
+    uint64_t* tmem_full = empty + TC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const GemmParams& g = p.g;
+    const int n0 = blockIdx.x * TC_BN;
+    const int b = blockIdx.y / p.tiles_per_utt, t0 = (blockIdx.y - b * p.tiles_per_utt) * TC_BM;
+    const int kblocks = (g.K + TC_BK - 1) / TC_BK, nk = kblocks * g.taps, pad = g.taps >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
+        tc_mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_w) : "memory");
+    }
+    if (warp == 1) {                                     // TMEM: 128 columns x 128 lanes fp32 accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(TC_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                 // ---------------- TMA producer
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % TC_STAGES; const uint32_t use = i / TC_STAGES;
+                if (use > 0) tc_mbar_wait(&empty[s], (use & 1) ^ 1);
+                const int tap = i / kblocks, kc = (i - tap * kblocks) * TC_BK;
+                unsigned char* a_dst = smem + s * TC_STAGE_BYTES;
+                tc_mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+                tc_tma_3d(a_dst, &p.tm_a, kc, t0 + tap - pad, b, &full[s]);            // rows outside [0, T): zero fill
+                tc_tma_2d(a_dst + TC_BM * TC_BK * 2, &p.tm_w, kc, tap * g.Nw + n0, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                 // ---------------- MMA issuer
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % TC_STAGES; const uint32_t use = i / TC_STAGES;
+                tc_mbar_wait(&full[s], use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = tc_smem_u32(smem + s * TC_STAGE_BYTES), b_addr = a_addr + TC_BM * TC_BK * 2;
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {   // advance 32 bytes (16 bf16) inside the 128-byte swizzle atom
+                    const uint64_t da = tc_smem_desc(a_addr + k * 32), db = tc_smem_desc(b_addr + k * 32);
+                    const uint32_t accum = (i | k) != 0;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem_base), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accum) : "memory");
+                }
+                // commit: the slot is free again once these MMAs have read it (implies fence::before_thread_sync)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&empty[s])) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(tmem_full)) : "memory");
+        }
+    } else {                                             // ---------------- epilogue warps 2..5
+        const int lg = warp & 3;                         // TMEM lane group this warp may access: lanes 32*lg .. 32*lg+31
+        tc_mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int t = t0 + lg * 32 + lane;
+        const int m = b * p.Tl + t;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                         "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (t < p.Tl && m < g.M) {
+                const int nb0 = n0 + c0;
+                const bool vec = g.scatter == SC_NONE && nb0 + 32 <= g.N && (g.ldo & 7) == 0 && (g.ldr & 7) == 0;
+                if (!vec) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2)
+                        gemm_store(g, m, nb0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                } else {                                 // thread = one output row: 32 consecutive columns, 16-byte accesses
+                    const int bb = m / g.T, tt = m - bb * g.T;
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (g.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb0 + j));
+                            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+                        }
+                    }
+                    if (g.resid_bf16) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(g.resid_bf16 + (size_t)m * g.ldr + nb0 + j);
+                            const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y), r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
+                            f[j] += r0.x; f[j + 1] += r0.y; f[j + 2] += r1.x; f[j + 3] += r1.y;
+                            f[j + 4] += r2.x; f[j + 5] += r2.y; f[j + 6] += r3.x; f[j + 7] += r3.y;
+                        }
+                    }
+                    if (g.resid_f32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 rv = *reinterpret_cast<const float4*>(g.resid_f32 + (size_t)m * g.ldr + nb0 + j);
+                            f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
+                        }
+                    }
+                    if (g.pe) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 pv = __ldg(reinterpret_cast<const float4*>(g.pe + (size_t)tt * kDModel + nb0 + j));
+                            f[j] += g.alpha * pv.x; f[j + 1] += g.alpha * pv.y; f[j + 2] += g.alpha * pv.z; f[j + 3] += g.alpha * pv.w;
+                        }
+                    }
+                    if (g.act == ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    } else if (g.act == ACT_TANH) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+                    }
+                    if (g.drop_site >= 0) {              // 32 aligned columns = one Philox word (P16)
+                        const uint4 w4 = philox4x32_10(make_uint4((uint32_t)g.drop_site, (uint32_t)tt, (uint32_t)(g.utt_offset + bb), (uint32_t)(nb0 >> 7)),
+                                                       (uint32_t)g.seed, (uint32_t)(g.seed >> 32));
+                        const uint32_t wi = (nb0 >> 5) & 3u;
+                        const uint32_t bits = wi == 0 ? w4.x : wi == 1 ? w4.y : wi == 2 ? w4.z : w4.w;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = ((bits >> j) & 1u) ? 2.f * f[j] : 0.f;
+                    }
+                    if (g.lens && tt >= g.lens[bb]) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+                    }
+                    if (g.out_f32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(g.out_f32 + (size_t)m * g.ldo + nb0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    }
+                    if (g.out_bf16) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            *reinterpret_cast<uint4*>(g.out_bf16 + (size_t)m * g.ldo + nb0 + j) =
+                                make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]), pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_BN) : "memory");
+    }
+}
+
+// host side ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TcEncodeFn tc_encode_fn() {
+    static TcEncodeFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TcEncodeFn>(f);
+    }
+    return fn;
+}
+
+// Same contract as launch_gemm (gemm_mma.cuh): g.A / g.W are bf16 row-major, lda / ldw in elements (multiples of 8),
+// W has taps * Nw rows (Nw = N rounded up to 128).  Returns cudaErrorInvalidValue for shapes it cannot describe.
+inline cudaError_t launch_gemm_tc(const GemmParams& g, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    TcEncodeFn enc = tc_encode_fn();
+    if (!enc || (g.lda & 7) || (g.ldw & 7) || (g.M % g.T) != 0) return cudaErrorInvalidValue;
+    GemmTcParams p;
+    p.g = g;
+    p.Tl = g.taps > 1 ? g.T : g.M;                       // plain GEMMs ignore the utterance structure when loading A
+    const int nb = g.M / p.Tl;
+    p.tiles_per_utt = (p.Tl + TC_BM - 1) / TC_BM;
+    const cuuint32_t estr[3] = {1, 1, 1};
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)p.Tl, (cuuint64_t)nb};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)g.lda * 2 * p.Tl};
+        const cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+        if (enc(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(g.A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.taps * g.Nw};
+        const cuuint64_t strides[1] = {(cuuint64_t)g.ldw * 2};
+        const cuuint32_t box[2] = {TC_BK, TC_BN};
+        if (enc(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(g.W), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    dim3 grid((g.N + TC_BN - 1) / TC_BN, nb * p.tiles_per_utt);
+    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+    ++launch_counter();
+    return cudaGetLastError();
+}
+
+}  // namespace tts

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "gemm_mma.cuh"
+#include "gemm_tc.cuh"
 #include "attention_mma.cuh"
 #include "misc_kernels.cuh"
 #include "decode_cluster.cuh"
@@ -429,28 +430,28 @@ static int run_encoder(TtsHandle* h, void* ws, const Ws& L, const int64_t* ph, c
     for (int i = 0; i < 3; ++i) {                                      // conv k5 + folded BN + ReLU + length mask
         GemmParams p = gp(x, 512, h->enc_conv_w[i], 512, M, 512, 512);
         p.taps = 5; p.T = S; p.bias = h->enc_conv_b[i]; p.act = ACT_RELU; p.lens = plens; p.out_bf16 = x2; p.ldo = 512;
-        CKL(launch_gemm(p, st));
+        CKL(launch_gemm_tc(p, st));
         std::swap(x, x2);
     }
     {   // linear + alpha * PE
         GemmParams p = gp(x, 512, h->enc_proj_w, 512, M, 512, 512);
         p.T = S; p.bias = h->enc_proj_b; p.pe = h->pe; p.alpha = h->enc_alpha; p.out_bf16 = x2; p.ldo = 512;
-        CKL(launch_gemm(p, st));
+        CKL(launch_gemm_tc(p, st));
         std::swap(x, x2);
     }
     for (int l = 0; l < 6; ++l) {
         auto& W = h->enc[l];
         GemmParams p = gp(x, 512, W.wqkv, 512, M, 1536, 512); p.bias = W.bqkv; p.out_bf16 = wide; p.ldo = 1536;
-        CKL(launch_gemm(p, st));
+        CKL(launch_gemm_tc(p, st));
         AttnParams at = ap_packed(wide, 1536, wide + 512, 1536, wide + 1024, 1536, a, 512, B, S, S, plens, 0);
         CKL(launch_flash_attn(at, st));
         p = gp(a, 512, W.wo, 512, M, 512, 512); p.bias = W.bo; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
-        CKL(launch_gemm(p, st));
+        CKL(launch_gemm_tc(p, st));
         CKL(layernorm(y, W.ln1g, W.ln1b, x, nullptr, M, h->cfg.ln_eps, st));
         p = gp(x, 512, W.w1, 512, M, 2048, 512); p.bias = W.b1; p.act = ACT_RELU; p.out_bf16 = wide; p.ldo = 2048;
-        CKL(launch_gemm(p, st));
+        CKL(launch_gemm_tc(p, st));
         p = gp(wide, 2048, W.w2, 2048, M, 512, 2048); p.bias = W.b2; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
-        CKL(launch_gemm(p, st));
+        CKL(launch_gemm_tc(p, st));
         CKL(layernorm(y, W.ln2g, W.ln2b, x, nullptr, M, h->cfg.ln_eps, st));
     }
     if (x != wsp<bf16>(ws, L.x)) {                                     // keep memory in ws.x
@@ -461,7 +462,7 @@ static int run_encoder(TtsHandle* h, void* ws, const Ws& L, const int64_t* ph, c
         // rows S..Spad of every (layer, b, h) stay zero: the decode kernel copies whole 16-row V blocks
         CKL(cudaMemsetAsync(wsp<bf16>(ws, L.cross_kv), 0, (size_t)6 * 2 * B * kHeads * L.Spad * kDHead * 2, st));
         p.T = S; p.B = B; p.Lpad = L.Spad; p.bias = h->ckv_b; p.scatter = v_blocked ? SC_CROSS_KV_VT : SC_CROSS_KV; p.out_bf16 = wsp<bf16>(ws, L.cross_kv);
-        CKL(launch_gemm(p, st));
+        CKL(launch_gemm_tc(p, st));
     }
     return 0;
 }
@@ -477,7 +478,7 @@ static int run_postnet(TtsHandle* h, void* ws, const Ws& L, const int* mlens, in
         p.taps = 5; p.T = T; p.bias = h->post_b[i]; p.lens = mlens;
         if (i < 4) { p.act = ACT_TANH; p.out_bf16 = x; p.ldo = 512; }
         else { p.resid_f32 = wsp<float>(ws, L.mel32); p.ldr = 80; p.out_f32 = mel_after; p.ldo = 80; }
-        CKL(launch_gemm(p, st));
+        CKL(launch_gemm_tc(p, st));
         in = x; std::swap(x, x2);
     }
     return 0;
@@ -697,44 +698,44 @@ extern "C" int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, cons
     {   // decoder prenet: dropout ALWAYS on (P7), masks keyed by (site, t, global utterance id)
         GemmParams p = gp(mel16, 96, h->pre_fc1, 96, M, 256, 96);
         p.T = T; p.bias = h->pre_b1; p.act = ACT_RELU; p.drop_site = SITE_DEC_PRENET_FC1; p.seed = seed; p.utt_offset = utt_offset; p.out_bf16 = x; p.ldo = 256;
-        CK(launch_gemm(p, st));
+        CK(launch_gemm_tc(p, st));
         p = gp(x, 256, h->pre_fc2, 256, M, 256, 256);
         p.T = T; p.bias = h->pre_b2; p.act = ACT_RELU; p.drop_site = SITE_DEC_PRENET_FC2; p.seed = seed; p.utt_offset = utt_offset; p.out_bf16 = x2; p.ldo = 256;
-        CK(launch_gemm(p, st));
+        CK(launch_gemm_tc(p, st));
         p = gp(x2, 256, h->pre_proj, 256, M, 512, 256);
         p.T = T; p.bias = h->pre_bp; p.pe = h->pe; p.alpha = h->dec_alpha; p.out_bf16 = x; p.ldo = 512;
-        CK(launch_gemm(p, st));
+        CK(launch_gemm_tc(p, st));
     }
     const bf16* ckv = wsp<bf16>(ws, L.cross_kv);
     const size_t ckv_layer = (size_t)B * kHeads * L.Spad * kDHead;
     for (int l = 0; l < 6; ++l) {
         auto& W = h->dec[l];
         GemmParams p = gp(x, 512, W.wqkv, 512, M, 1536, 512); p.bias = W.bqkv; p.out_bf16 = wide; p.ldo = 1536;
-        CK(launch_gemm(p, st));
+        CK(launch_gemm_tc(p, st));
         AttnParams at = ap_packed(wide, 1536, wide + 512, 1536, wide + 1024, 1536, a, 512, B, T, T, mel_lens, 1);
         CK(launch_flash_attn(at, st));
         p = gp(a, 512, W.wo, 512, M, 512, 512); p.bias = W.bo; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
-        CK(launch_gemm(p, st));
+        CK(launch_gemm_tc(p, st));
         CK(layernorm(y, W.ln1g, W.ln1b, x, nullptr, M, h->cfg.ln_eps, st));
         p = gp(x, 512, W.wq2, 512, M, 512, 512); p.bias = W.bq2; p.out_bf16 = x2; p.ldo = 512;
-        CK(launch_gemm(p, st));
+        CK(launch_gemm_tc(p, st));
         at = ap_packed(x2, 512, nullptr, 64, nullptr, 64, a, 512, B, T, S, phoneme_lens, 0);
         at.K = ckv + (size_t)(l * 2) * ckv_layer; at.V = ckv + (size_t)(l * 2 + 1) * ckv_layer;     // [B][H][S][64]
         at.k_bs = at.v_bs = (long)kHeads * L.Spad * kDHead; at.k_hs = at.v_hs = (long)L.Spad * kDHead; at.k_rs = at.v_rs = kDHead;
         CK(launch_flash_attn(at, st));
         p = gp(a, 512, W.wo2, 512, M, 512, 512); p.bias = W.bo2; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
-        CK(launch_gemm(p, st));
+        CK(launch_gemm_tc(p, st));
         CK(layernorm(y, W.ln2g, W.ln2b, x, nullptr, M, h->cfg.ln_eps, st));
         p = gp(x, 512, W.w1, 512, M, 2048, 512); p.bias = W.b1; p.act = ACT_RELU; p.out_bf16 = wide; p.ldo = 2048;
-        CK(launch_gemm(p, st));
+        CK(launch_gemm_tc(p, st));
         p = gp(wide, 2048, W.w2, 2048, M, 512, 2048); p.bias = W.b2; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
-        CK(launch_gemm(p, st));
+        CK(launch_gemm_tc(p, st));
         CK(layernorm(y, W.ln3g, W.ln3b, x, nullptr, M, h->cfg.ln_eps, st));
     }
     {   // [mel | stop] heads, zeroed past mel_lens
         GemmParams p = gp(x, 512, h->head_w, 512, M, 81, 512);
         p.T = T; p.bias = h->head_b; p.lens = mel_lens; p.scatter = SC_HEAD; p.out_f32 = mel_before; p.out2_f32 = stop_logits;
-        CK(launch_gemm(p, st));
+        CK(launch_gemm_tc(p, st));
     }
     {
         const int n = M * 24;
@@ -769,6 +770,19 @@ extern "C" int tts_k_conv5(const void* X, const void* W, const float* bias, cons
     GemmParams p = gp((const bf16*)X, Cin, (const bf16*)W, Cin, B * T, Cout, Cin);
     p.taps = 5; p.T = T; p.bias = bias; p.act = act; p.lens = lens; p.out_f32 = Y; p.ldo = Cout;
     return (int)launch_gemm(p, (cudaStream_t)stream);
+}
+extern "C" int tts_k_gemm_tc(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int act, void* stream) {
+    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 128)) return TTS_E_ARG;
+    GemmParams p = gp((const bf16*)A, K, (const bf16*)W, K, M, N, K);
+    p.bias = bias; p.act = act; p.out_f32 = C; p.ldo = N;
+    return (int)launch_gemm_tc(p, (cudaStream_t)stream);
+}
+extern "C" int tts_k_conv5_tc(const void* X, const void* W, const float* bias, const int32_t* lens, float* Y, int B, int T, int Cin,
+                              int Cout, int act, void* stream) {
+    if (!X || !W || !Y || B <= 0 || T <= 0 || (Cin % 8) || (Cout % 128)) return TTS_E_ARG;
+    GemmParams p = gp((const bf16*)X, Cin, (const bf16*)W, Cin, B * T, Cout, Cin);
+    p.taps = 5; p.T = T; p.bias = bias; p.act = act; p.lens = lens; p.out_f32 = Y; p.ldo = Cout;
+    return (int)launch_gemm_tc(p, (cudaStream_t)stream);
 }
 extern "C" int tts_k_attention(const void* Q, const void* K, const void* V, void* O, const int32_t* klens, int B, int H, int Lq,
                                int Lk, int causal, void* stream) {

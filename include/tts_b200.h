@@ -109,15 +109,11 @@ int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* 
 int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long long* out, int n_steps, void* stream);
 
 /* ---- per-kernel entry points (tests/test_gpu_kernels.py; not part of the drop-in surface) ---- */
-/* C[M][N] = act(A[M][K] . W[N][K]^T + bias) ; bf16 in, fp32 out; act 0 none / 1 relu / 2 tanh. */
+/* C[M][N] = act(A[M][K] . W[N][K]^T + bias) ; bf16 in, fp32 out; act 0 none / 1 relu / 2 tanh (tcgen05 kernel, gemm_tc.cuh). */
 int tts_k_gemm(const void* A_bf16, const void* W_bf16, const float* bias, float* C, int M, int N, int K, int act, void* stream);
 /* conv1d(k=5, pad=2) over [B][T][Cin] with W [5][Cout][Cin] bf16 -> fp32 [B][T][Cout]; rows t >= lens[b] zeroed. */
 int tts_k_conv5(const void* X_bf16, const void* W_bf16, const float* bias, const int32_t* lens, float* Y,
                 int B, int T, int Cin, int Cout, int act, void* stream);
-/* The same two ops on the tcgen05 / TMEM / TMA kernel (gemm_tc.cuh). */
-int tts_k_gemm_tc(const void* A_bf16, const void* W_bf16, const float* bias, float* C, int M, int N, int K, int act, void* stream);
-int tts_k_conv5_tc(const void* X_bf16, const void* W_bf16, const float* bias, const int32_t* lens, float* Y,
-                   int B, int T, int Cin, int Cout, int act, void* stream);
 /* Attention core: Q [B][Lq][H*64], K/V [B][Lk][H*64] bf16 -> O [B][Lq][H*64] bf16. */
 int tts_k_attention(const void* Q, const void* K, const void* V, void* O, const int32_t* klens,
                     int B, int H, int Lq, int Lk, int causal, void* stream);

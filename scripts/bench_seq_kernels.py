@@ -33,7 +33,7 @@ def timeit(fn, iters=20):
 
 
 out = []
-for name, fn_name in (("tcgen05", "tts_k_gemm_tc"), ("mma.sync", "tts_k_gemm")):
+for name, fn_name in (("tcgen05", "tts_k_gemm"),):
     if not hasattr(lib, fn_name):
         continue
     for (M, N, K) in [(25600, 1536, 512), (25600, 2048, 512), (25600, 512, 2048), (51200, 512, 512), (6400, 6144, 512)]:
@@ -43,7 +43,7 @@ for name, fn_name in (("tcgen05", "tts_k_gemm_tc"), ("mma.sync", "tts_k_gemm")):
         tf = 2.0 * M * N * K / ms / 1e9
         out.append(dict(kernel=f"gemm {name}", M=M, N=N, K=K, ms=ms, tflops=tf, frac_of_measured_peak=tf / PEAK))
         print(f"gemm {name:9s} M={M:6d} N={N:5d} K={K:5d}: {ms:7.3f} ms  {tf:7.1f} TFLOP/s  ({tf / PEAK:.1%} of {PEAK:.0f})")
-for name, fn_name in (("tcgen05", "tts_k_conv5_tc"), ("mma.sync", "tts_k_conv5")):
+for name, fn_name in (("tcgen05", "tts_k_conv5"),):
     if not hasattr(lib, fn_name):
         continue
     B, T, Cin, Cout = 64, 800, 512, 512

@@ -30,14 +30,13 @@ def _stream():
 
 @pytest.mark.parametrize("M,N,K,act", [(128, 128, 32, 0), (300, 512, 512, 1), (1, 128, 96, 0), (777, 1536, 512, 0),
                                          (130, 512, 2048, 2), (6400, 256, 256, 1)])
-@pytest.mark.parametrize("impl", ["tts_k_gemm", "tts_k_gemm_tc"])
-def test_gemm(lib, M, N, K, act, impl):
+def test_gemm(lib, M, N, K, act):
     g = torch.Generator().manual_seed(M + N + K)
     A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
     W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
     bias = torch.randn(N, generator=g).cuda()
     Cout = torch.empty(M, N, device="cuda")
-    rc = getattr(lib, impl)(_p(A), _p(W), _p(bias), _p(Cout), M, N, K, act, _stream())
+    rc = lib.tts_k_gemm(_p(A), _p(W), _p(bias), _p(Cout), M, N, K, act, _stream())
     assert rc == 0
     ref = A.float() @ W.float().T + bias
     ref = torch.relu(ref) if act == 1 else torch.tanh(ref) if act == 2 else ref
@@ -46,8 +45,7 @@ def test_gemm(lib, M, N, K, act, impl):
 
 
 @pytest.mark.parametrize("B,T,Cin,Cout", [(2, 37, 96, 512), (3, 130, 512, 512), (1, 5, 512, 128), (4, 64, 512, 128)])
-@pytest.mark.parametrize("impl", ["tts_k_conv5", "tts_k_conv5_tc"])
-def test_conv5(lib, B, T, Cin, Cout, impl):
+def test_conv5(lib, B, T, Cin, Cout):
     g = torch.Generator().manual_seed(B * T)
     X = (torch.randn(B, T, Cin, generator=g) * 0.5).to(torch.bfloat16)
     Wt = (torch.randn(Cout, Cin, 5, generator=g) * 0.03).to(torch.bfloat16)
@@ -60,7 +58,7 @@ def test_conv5(lib, B, T, Cin, Cout, impl):
     Wp = Wt.permute(2, 0, 1).contiguous().cuda()           # [5][Cout][Cin]
     Xd = Xm.to(torch.bfloat16).cuda(); Y = torch.empty(B, T, Cout, device="cuda")
     bias_d, lens_d = bias.cuda(), lens.cuda()               # keep every device buffer alive across the call
-    rc = getattr(lib, impl)(_p(Xd), _p(Wp), _p(bias_d), _p(lens_d), _p(Y), B, T, Cin, Cout, 2, _stream())
+    rc = lib.tts_k_conv5(_p(Xd), _p(Wp), _p(bias_d), _p(lens_d), _p(Y), B, T, Cin, Cout, 2, _stream())
     assert rc == 0
     torch.cuda.synchronize()
     assert torch.allclose(Y.cpu(), ref, atol=3e-3, rtol=3e-3), float((Y.cpu() - ref).abs().max())

@@ -3,16 +3,17 @@
 // i.e. plain GEMMs (taps = 1, T = M) and conv1d(k = 5, pad = 2) as 5 row-shifted GEMMs accumulated into ONE
 // TMEM accumulator; rows outside [0, T) of their own utterance are zero-filled by TMA's out-of-bounds handling
 // (the A operand is a 3-D tensor map {channels, frames, utterances}), so no padded copies exist.
-// Structure (one 128 x 128 output tile per CTA, 192 threads):
+// Structure (persistent: one CTA per SM walks 128 x 128 output tiles; 192 threads; the TMEM accumulator is double-buffered
+// so the epilogue of tile i overlaps the mainloop of tile i+1):
 //   warp 0  : TMA producer      cp.async.bulk.tensor -> 4-stage shared-memory ring (128B swizzle), mbarrier full/empty
 //   warp 1  : MMA issuer        one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16), accumulator
 //                               in TMEM (128 fp32 columns); tcgen05.commit releases ring slots / signals the epilogue
-//   warps 2-5: epilogue         tcgen05.ld 32x32b (thread = output row) -> fused epilogue of gemm_mma.cuh (bias, BN fold,
+//   warps 2-5: epilogue         tcgen05.ld 32x32b (thread = output row) -> fused epilogue of gemm_epilogue.cuh (bias, BN fold,
 //                               ReLU / tanh, residual, alpha*PE, length mask, Philox dropout, KV scatter, head split)
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
-#include "gemm_mma.cuh"
+#include "gemm_epilogue.cuh"
 #include "philox.cuh"
 
 namespace tts {
@@ -28,6 +29,7 @@ struct GemmTcParams {
     GemmParams g;                     // shapes + epilogue (A / W pointers unused here)
     int Tl;                           // rows per A-tensor slab: T for convs (taps > 1), M for plain GEMMs
     int tiles_per_utt;                // ceil(Tl / 128)
+    int n_tiles_n, n_tiles;           // tiles along N; total tiles (persistent CTAs walk tile = blockIdx.x + i * gridDim.x)
 };
 
 TTS_D uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,23 +65,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* empty = full + TC_STAGES;
-    uint64_t* tmem_full = empty + TC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty + TC_STAGES;             // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GemmParams& g = p.g;
-    const int n0 = blockIdx.x * TC_BN;
-    const int b = blockIdx.y / p.tiles_per_utt, t0 = (blockIdx.y - b * p.tiles_per_utt) * TC_BM;
     const int kblocks = (g.K + TC_BK - 1) / TC_BK, nk = kblocks * g.taps, pad = g.taps >> 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
-        tc_mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_w) : "memory");
     }
-    if (warp == 1) {                                     // TMEM: 128 columns x 128 lanes fp32 accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(TC_BN) : "memory");
+    if (warp == 1) {                                     // TMEM: 2 x 128 columns x 128 lanes fp32 (double-buffered accumulator)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(2 * TC_BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -89,45 +90,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {                                 // ---------------- TMA producer
-            for (int i = 0; i < nk; ++i) {
-                const int s = i % TC_STAGES; const uint32_t use = i / TC_STAGES;
-                if (use > 0) tc_mbar_wait(&empty[s], (use & 1) ^ 1);
-                const int tap = i / kblocks, kc = (i - tap * kblocks) * TC_BK;
-                unsigned char* a_dst = smem + s * TC_STAGE_BYTES;
-                tc_mbar_expect_tx(&full[s], TC_STAGE_BYTES);
-                tc_tma_3d(a_dst, &p.tm_a, kc, t0 + tap - pad, b, &full[s]);            // rows outside [0, T): zero fill
-                tc_tma_2d(a_dst + TC_BM * TC_BK * 2, &p.tm_w, kc, tap * g.Nw + n0, &full[s]);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * TC_BN;
+                const int b = mt / p.tiles_per_utt, t0 = (mt - b * p.tiles_per_utt) * TC_BM;
+                for (int i = 0; i < nk; ++i, ++it) {
+                    const int s = it % TC_STAGES; const uint32_t use = it / TC_STAGES;
+                    if (use > 0) tc_mbar_wait(&empty[s], (use & 1) ^ 1);
+                    const int tap = i / kblocks, kc = (i - tap * kblocks) * TC_BK;
+                    unsigned char* a_dst = smem + s * TC_STAGE_BYTES;
+                    tc_mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+                    tc_tma_3d(a_dst, &p.tm_a, kc, t0 + tap - pad, b, &full[s]);        // rows outside [0, T): zero fill
+                    tc_tma_2d(a_dst + TC_BM * TC_BK * 2, &p.tm_w, kc, tap * g.Nw + n0, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                 // ---------------- MMA issuer
-            for (int i = 0; i < nk; ++i) {
-                const int s = i % TC_STAGES; const uint32_t use = i / TC_STAGES;
-                tc_mbar_wait(&full[s], use & 1);
+            uint32_t it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
+                const uint32_t acc = j & 1, ause = j >> 1;
+                if (ause > 0) tc_mbar_wait(&tmem_empty[acc], (ause & 1) ^ 1);           // epilogue drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = tc_smem_u32(smem + s * TC_STAGE_BYTES), b_addr = a_addr + TC_BM * TC_BK * 2;
+                const uint32_t d_tmem = tmem_base + acc * TC_BN;
+                for (int i = 0; i < nk; ++i, ++it) {
+                    const int s = it % TC_STAGES; const uint32_t use = it / TC_STAGES;
+                    tc_mbar_wait(&full[s], use & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = tc_smem_u32(smem + s * TC_STAGE_BYTES), b_addr = a_addr + TC_BM * TC_BK * 2;
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {   // advance 32 bytes (16 bf16) inside the 128-byte swizzle atom
-                    const uint64_t da = tc_smem_desc(a_addr + k * 32), db = tc_smem_desc(b_addr + k * 32);
-                    const uint32_t accum = (i | k) != 0;
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                                 ::"r"(tmem_base), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accum) : "memory");
+                    for (int k = 0; k < TC_BK / 16; ++k) {   // advance 32 bytes (16 bf16) inside the 128-byte swizzle atom
+                        const uint64_t da = tc_smem_desc(a_addr + k * 32), db = tc_smem_desc(b_addr + k * 32);
+                        const uint32_t accum = (i | k) != 0;
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(d_tmem), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accum) : "memory");
+                    }
+                    // commit: the slot is free again once these MMAs have read it (implies fence::before_thread_sync)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&empty[s])) : "memory");
                 }
-                // commit: the slot is free again once these MMAs have read it (implies fence::before_thread_sync)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&empty[s])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&tmem_full[acc])) : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(tmem_full)) : "memory");
         }
     } else {                                             // ---------------- epilogue warps 2..5
         const int lg = warp & 3;                         // TMEM lane group this warp may access: lanes 32*lg .. 32*lg+31
-        tc_mbar_wait(tmem_full, 0);
+        uint32_t j = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
+        const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * TC_BN;
+        const int b = mt / p.tiles_per_utt, t0 = (mt - b * p.tiles_per_utt) * TC_BM;
+        const uint32_t acc = j & 1;
+        tc_mbar_wait(&tmem_full[acc], (j >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int t = t0 + lg * 32 + lane;
         const int m = b * p.Tl + t;
 #pragma unroll 1
         for (int c0 = 0; c0 < TC_BN; c0 += 32) {
             uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
                          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -212,11 +230,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&tmem_empty[acc])) : "memory");   // accumulator free
+        }
     }
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_BN) : "memory");
     }
 }
 
@@ -234,7 +255,7 @@ inline TcEncodeFn tc_encode_fn() {
     return fn;
 }
 
-// Same contract as launch_gemm (gemm_mma.cuh): g.A / g.W are bf16 row-major, lda / ldw in elements (multiples of 8),
+// Same contract as launch_gemm (gemm_epilogue.cuh): g.A / g.W are bf16 row-major, lda / ldw in elements (multiples of 8),
 // W has taps * Nw rows (Nw = N rounded up to 128).  Returns cudaErrorInvalidValue for shapes it cannot describe.
 inline cudaError_t launch_gemm_tc(const GemmParams& g, cudaStream_t stream) {
     static bool attr_set = false;
@@ -267,7 +288,11 @@ inline cudaError_t launch_gemm_tc(const GemmParams& g, cudaStream_t stream) {
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
-    dim3 grid((g.N + TC_BN - 1) / TC_BN, nb * p.tiles_per_utt);
+    p.n_tiles_n = (g.N + TC_BN - 1) / TC_BN;
+    p.n_tiles = p.n_tiles_n * nb * p.tiles_per_utt;
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;          // persistent: one CTA per SM, static round-robin tiles
     gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
     ++launch_counter();
     return cudaGetLastError();

@@ -14,7 +14,6 @@
 
 #include "common.cuh"
 #include "philox.cuh"
-#include "gemm_mma.cuh"
 #include "gemm_tc.cuh"
 #include "attention_mma.cuh"
 #include "misc_kernels.cuh"
@@ -759,25 +758,12 @@ extern "C" int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long 
 
 // per-kernel test entry points
 extern "C" int tts_k_gemm(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int act, void* stream) {
-    if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || (K % 32) || (N % 128)) return TTS_E_ARG;
-    GemmParams p = gp((const bf16*)A, K, (const bf16*)W, K, M, N, K);
-    p.bias = bias; p.act = act; p.out_f32 = C; p.ldo = N;
-    return (int)launch_gemm(p, (cudaStream_t)stream);
-}
-extern "C" int tts_k_conv5(const void* X, const void* W, const float* bias, const int32_t* lens, float* Y, int B, int T, int Cin,
-                           int Cout, int act, void* stream) {
-    if (!X || !W || !Y || B <= 0 || T <= 0 || (Cin % 32) || (Cout % 128)) return TTS_E_ARG;
-    GemmParams p = gp((const bf16*)X, Cin, (const bf16*)W, Cin, B * T, Cout, Cin);
-    p.taps = 5; p.T = T; p.bias = bias; p.act = act; p.lens = lens; p.out_f32 = Y; p.ldo = Cout;
-    return (int)launch_gemm(p, (cudaStream_t)stream);
-}
-extern "C" int tts_k_gemm_tc(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int act, void* stream) {
     if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 128)) return TTS_E_ARG;
     GemmParams p = gp((const bf16*)A, K, (const bf16*)W, K, M, N, K);
     p.bias = bias; p.act = act; p.out_f32 = C; p.ldo = N;
     return (int)launch_gemm_tc(p, (cudaStream_t)stream);
 }
-extern "C" int tts_k_conv5_tc(const void* X, const void* W, const float* bias, const int32_t* lens, float* Y, int B, int T, int Cin,
+extern "C" int tts_k_conv5(const void* X, const void* W, const float* bias, const int32_t* lens, float* Y, int B, int T, int Cin,
                               int Cout, int act, void* stream) {
     if (!X || !W || !Y || B <= 0 || T <= 0 || (Cin % 8) || (Cout % 128)) return TTS_E_ARG;
     GemmParams p = gp((const bf16*)X, Cin, (const bf16*)W, Cin, B * T, Cout, Cin);

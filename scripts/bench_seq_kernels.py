@@ -53,7 +53,7 @@ for name, fn_name in (("tcgen05", "tts_k_conv5"),):
     tf = 2.0 * B * T * Cout * Cin * 5 / ms / 1e9
     out.append(dict(kernel=f"conv5 {name}", B=B, T=T, Cin=Cin, Cout=Cout, ms=ms, tflops=tf, frac_of_measured_peak=tf / PEAK))
     print(f"conv5 {name:9s} B={B} T={T} {Cin}->{Cout}: {ms:7.3f} ms  {tf:7.1f} TFLOP/s  ({tf / PEAK:.1%})")
-for (B, L, causal) in [(32, 400, 1), (32, 800, 1), (16, 1600, 1), (64, 100, 0)]:
+for (B, L, causal) in [(32, 400, 1), (32, 800, 1), (16, 1600, 1), (64, 100, 0), (64, 800, 1), (32, 800, 0), (8, 4096, 0)]:
     H = 8
     Q = torch.randn(B, L, H * 64, device="cuda").to(torch.bfloat16); K_ = torch.randn_like(Q); V = torch.randn_like(Q); O = torch.empty_like(Q)
     kl = torch.full((B,), L, dtype=torch.int32, device="cuda")

@@ -15,7 +15,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "gemm_tc.cuh"
-#include "attention_mma.cuh"
+#include "attention_tc.cuh"
 #include "misc_kernels.cuh"
 #include "decode_cluster.cuh"
 
@@ -443,7 +443,7 @@ static int run_encoder(TtsHandle* h, void* ws, const Ws& L, const int64_t* ph, c
         GemmParams p = gp(x, 512, W.wqkv, 512, M, 1536, 512); p.bias = W.bqkv; p.out_bf16 = wide; p.ldo = 1536;
         CKL(launch_gemm_tc(p, st));
         AttnParams at = ap_packed(wide, 1536, wide + 512, 1536, wide + 1024, 1536, a, 512, B, S, S, plens, 0);
-        CKL(launch_flash_attn(at, st));
+        CKL(launch_flash_attn_tc(at, st));
         p = gp(a, 512, W.wo, 512, M, 512, 512); p.bias = W.bo; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
         CKL(launch_gemm_tc(p, st));
         CKL(layernorm(y, W.ln1g, W.ln1b, x, nullptr, M, h->cfg.ln_eps, st));
@@ -712,7 +712,7 @@ extern "C" int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, cons
         GemmParams p = gp(x, 512, W.wqkv, 512, M, 1536, 512); p.bias = W.bqkv; p.out_bf16 = wide; p.ldo = 1536;
         CK(launch_gemm_tc(p, st));
         AttnParams at = ap_packed(wide, 1536, wide + 512, 1536, wide + 1024, 1536, a, 512, B, T, T, mel_lens, 1);
-        CK(launch_flash_attn(at, st));
+        CK(launch_flash_attn_tc(at, st));
         p = gp(a, 512, W.wo, 512, M, 512, 512); p.bias = W.bo; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
         CK(launch_gemm_tc(p, st));
         CK(layernorm(y, W.ln1g, W.ln1b, x, nullptr, M, h->cfg.ln_eps, st));
@@ -721,7 +721,7 @@ extern "C" int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, cons
         at = ap_packed(x2, 512, nullptr, 64, nullptr, 64, a, 512, B, T, S, phoneme_lens, 0);
         at.K = ckv + (size_t)(l * 2) * ckv_layer; at.V = ckv + (size_t)(l * 2 + 1) * ckv_layer;     // [B][H][S][64]
         at.k_bs = at.v_bs = (long)kHeads * L.Spad * kDHead; at.k_hs = at.v_hs = (long)L.Spad * kDHead; at.k_rs = at.v_rs = kDHead;
-        CK(launch_flash_attn(at, st));
+        CK(launch_flash_attn_tc(at, st));
         p = gp(a, 512, W.wo2, 512, M, 512, 512); p.bias = W.bo2; p.resid_bf16 = x; p.ldr = 512; p.out_f32 = y; p.ldo = 512;
         CK(launch_gemm_tc(p, st));
         CK(layernorm(y, W.ln2g, W.ln2b, x, nullptr, M, h->cfg.ln_eps, st));
@@ -776,7 +776,7 @@ extern "C" int tts_k_attention(const void* Q, const void* K, const void* V, void
     const int ld = H * 64;
     AttnParams a = ap_packed((const bf16*)Q, ld, (const bf16*)K, ld, (const bf16*)V, ld, (bf16*)O, ld, B, Lq, Lk, klens, causal);
     a.H = H;
-    return (int)launch_flash_attn(a, (cudaStream_t)stream);
+    return (int)launch_flash_attn_tc(a, (cudaStream_t)stream);
 }
 extern "C" int tts_k_layernorm(const float* X, const float* gamma, const float* beta, void* Y, int M, float eps, void* stream) {
     if (!X || !gamma || !beta || !Y || M <= 0) return TTS_E_ARG;

@@ -117,6 +117,14 @@ int tts_k_conv5(const void* X_bf16, const void* W_bf16, const float* bias, const
 /* Attention core: Q [B][Lq][H*64], K/V [B][Lk][H*64] bf16 -> O [B][Lq][H*64] bf16. */
 int tts_k_attention(const void* Q, const void* K, const void* V, void* O, const int32_t* klens,
                     int B, int H, int Lq, int Lk, int causal, void* stream);
+/* Attention core with the per-row log-sum-exp kept for the backward pass: lse [B][H][Lq] fp32 (log2 domain). */
+int tts_k_attention_lse(const void* Q, const void* K, const void* V, void* O, float* lse, const int32_t* klens,
+                        int B, int H, int Lq, int Lk, int causal, void* stream);
+/* Attention backward (training path): Q/K/V/O/dO as above + lse -> dQ/dK/dV bf16 in the same layouts.
+ * scratch: fp32 [B*Lq*H*64 + B*H*Lq] device buffer. */
+int tts_k_attention_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse,
+                        const int32_t* klens, void* dQ, void* dK, void* dV, float* scratch,
+                        int B, int H, int Lq, int Lk, int causal, void* stream);
 /* LayerNorm over rows of 512: fp32 in -> bf16 out. */
 int tts_k_layernorm(const float* X, const float* gamma, const float* beta, void* Y_bf16, int M, float eps, void* stream);
 /* Keep-bits of a p = 0.5 dropout site: out[t][b][c] (uint8) for t < T, b < B, c < C. */

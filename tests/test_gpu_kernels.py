@@ -90,6 +90,44 @@ def test_attention(lib, B, Lq, Lk, causal):
     assert torch.allclose(got, ref, atol=2e-2, rtol=2e-2), float((got - ref).abs().max())
 
 
+@pytest.mark.parametrize("B,Lq,Lk,causal", [(2, 100, 100, 0), (2, 129, 129, 1), (1, 400, 400, 1), (2, 200, 37, 0), (1, 64, 300, 0),
+                                             (2, 260, 260, 1)])
+def test_attention_backward(lib, B, Lq, Lk, causal):
+    """dQ / dK / dV of the tcgen05 backward kernel against torch autograd (fp32) on the same bf16 inputs."""
+    H = 8
+    g = torch.Generator().manual_seed(Lq * 11 + Lk)
+    Q = torch.randn(B, Lq, H * 64, generator=g).to(torch.bfloat16)
+    K = torch.randn(B, Lk, H * 64, generator=g).to(torch.bfloat16)
+    V = torch.randn(B, Lk, H * 64, generator=g).to(torch.bfloat16)
+    dO = torch.randn(B, Lq, H * 64, generator=g).to(torch.bfloat16)
+    klens = torch.randint(1, Lk + 1, (B,), generator=g, dtype=torch.int32); klens[0] = Lk
+    qf, kf, vf = (x.float().requires_grad_(True) for x in (Q, K, V))
+    q = qf.view(B, Lq, H, 64).transpose(1, 2); k = kf.view(B, Lk, H, 64).transpose(1, 2); v = vf.view(B, Lk, H, 64).transpose(1, 2)
+    s = q @ k.transpose(-1, -2) / 8.0
+    mask = (torch.arange(Lk)[None, :] < klens[:, None])[:, None, None, :]
+    if causal:
+        mask = mask & torch.tril(torch.ones(Lq, Lk, dtype=torch.bool))[None, None]
+    s = s.masked_fill(~mask, float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, Lq, H * 64)
+    ref.backward(dO.float())
+    Qd, Kd, Vd, dOd, kl = Q.cuda(), K.cuda(), V.cuda(), dO.cuda(), klens.cuda()
+    O = torch.empty_like(Qd); lse = torch.empty(B, H, Lq, device="cuda")
+    assert lib.tts_k_attention_lse(_p(Qd), _p(Kd), _p(Vd), _p(O), _p(lse), _p(kl), B, H, Lq, Lk, causal, _stream()) == 0
+    dQ, dK, dV = torch.empty_like(Qd), torch.empty_like(Kd), torch.empty_like(Vd)
+    scratch = torch.empty(B * Lq * H * 64 + B * H * Lq, device="cuda")
+    rc = lib.tts_k_attention_bwd(_p(Qd), _p(Kd), _p(Vd), _p(O), _p(dOd), _p(lse), _p(kl), _p(dQ), _p(dK), _p(dV), _p(scratch),
+                                 B, H, Lq, Lk, causal, _stream())
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref_lse = torch.logsumexp(s, -1) * 1.4426950408889634
+    assert torch.allclose(lse.cpu(), ref_lse, atol=2e-2, rtol=1e-3)
+    for name, got, want in (("dQ", dQ, qf.grad), ("dK", dK, kf.grad), ("dV", dV, vf.grad)):
+        got = got.float().cpu()
+        err = float((got - want).norm() / want.norm())
+        assert err < 2e-2, (name, err)                       # bf16 P / dS operands: ~1e-2 relative
+        assert torch.allclose(got, want, atol=6e-2, rtol=6e-2), (name, float((got - want).abs().max()))
+
+
 def test_layernorm(lib):
     g = torch.Generator().manual_seed(3)
     X = torch.randn(333, 512, generator=g) * 3 + 1

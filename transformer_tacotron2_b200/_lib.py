@@ -42,6 +42,8 @@ SIGNATURES = {
     "tts_k_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "tts_k_conv5": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "tts_k_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "tts_k_attention_lse": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "tts_k_attention_bwd": (_I, [_P] * 11 + [_I, _I, _I, _I, _I, _P]),
     "tts_k_layernorm": (_I, [_P, _P, _P, _P, _I, C.c_float, _P]),
     "tts_k_philox_bits": (_I, [_U64, _I, _I, _I, _I, _I, _P, _P]),
 }

@@ -27,6 +27,7 @@ struct AttnParams {
     const int* klens;     // keys >= klens[b] are masked (null: all Lk valid)
     int causal;
     float scale_log2;     // (1/sqrt(dh)) * log2(e)
+    float* lse;           // optional [B][H][Lq]: log2-domain log-sum-exp of the scaled scores (kept for the backward pass)
 };
 
 constexpr int FT_BM = 128, FT_BN = 128, FT_THREADS = 192;
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) flash_attn_tc_kernel(const __gr
         ft_ld_wait();
         if (qi < a.Lq) {
             const float inv = l > 0.f ? 1.f / l : 0.f;
+            if (a.lse) a.lse[((long)b * a.H + h) * a.Lq + qi] = l > 0.f ? m + log2f(l) : INFINITY;
             bf16* og = a.O + b * a.o_bs + h * a.o_hs + (long)qi * a.o_rs;
 #pragma unroll
             for (int i = 0; i < 64; i += 8)
@@ -280,6 +282,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) flash_attn_tc_kernel(const __gr
     } else {                                             // no visible key at all (klen == 0): zeros
         const int r = (warp & 3) * 32 + lane, qi = q0 + r;
         if (qi < a.Lq) {
+            if (a.lse) a.lse[((long)b * a.H + h) * a.Lq + qi] = INFINITY;
             bf16* og = a.O + b * a.o_bs + h * a.o_hs + (long)qi * a.o_rs;
 #pragma unroll
             for (int i = 0; i < 64; i += 8) *reinterpret_cast<uint4*>(og + i) = make_uint4(0, 0, 0, 0);

@@ -16,6 +16,7 @@
 #include "philox.cuh"
 #include "gemm_tc.cuh"
 #include "attention_tc.cuh"
+#include "attention_bwd_tc.cuh"
 #include "misc_kernels.cuh"
 #include "decode_cluster.cuh"
 
@@ -777,6 +778,59 @@ extern "C" int tts_k_attention(const void* Q, const void* K, const void* V, void
     AttnParams a = ap_packed((const bf16*)Q, ld, (const bf16*)K, ld, (const bf16*)V, ld, (bf16*)O, ld, B, Lq, Lk, klens, causal);
     a.H = H;
     return (int)launch_flash_attn_tc(a, (cudaStream_t)stream);
+}
+extern "C" int tts_k_attention_lse(const void* Q, const void* K, const void* V, void* O, float* lse, const int32_t* klens, int B, int H,
+                                   int Lq, int Lk, int causal, void* stream) {
+    if (!Q || !K || !V || !O || !lse || B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return TTS_E_ARG;
+    const int ld = H * 64;
+    AttnParams a = ap_packed((const bf16*)Q, ld, (const bf16*)K, ld, (const bf16*)V, ld, (bf16*)O, ld, B, Lq, Lk, klens, causal);
+    a.H = H; a.lse = lse;
+    return (int)launch_flash_attn_tc(a, (cudaStream_t)stream);
+}
+namespace {
+// fp32 -> bf16 rows (dQ accumulator -> operand)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long n4) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+AttnBwdParams abp_packed(const AttnParams& f, const bf16* dO, const float* lse, const float* dsum, float* dQ, int lddq, bf16* dK, int lddk,
+                         bf16* dV, int lddv) {
+    AttnBwdParams a; memset(&a, 0, sizeof(a));
+    a.Q = f.Q; a.K = f.K; a.V = f.V; a.dO = dO;
+    a.q_bs = f.q_bs; a.q_hs = f.q_hs; a.q_rs = f.q_rs; a.k_bs = f.k_bs; a.k_hs = f.k_hs; a.k_rs = f.k_rs;
+    a.v_bs = f.v_bs; a.v_hs = f.v_hs; a.v_rs = f.v_rs; a.o_bs = f.o_bs; a.o_hs = f.o_hs; a.o_rs = f.o_rs;
+    a.lse = lse; a.dsum = dsum;
+    a.dQ = dQ; a.dq_bs = (long)f.Lq * lddq; a.dq_hs = 64; a.dq_rs = lddq;
+    a.dK = dK; a.dk_bs = (long)f.Lk * lddk; a.dk_hs = 64; a.dk_rs = lddk;
+    a.dV = dV; a.dv_bs = (long)f.Lk * lddv; a.dv_hs = 64; a.dv_rs = lddv;
+    a.B = f.B; a.H = f.H; a.Lq = f.Lq; a.Lk = f.Lk; a.klens = f.klens; a.causal = f.causal;
+    a.scale_log2 = f.scale_log2; a.scale = 0.125f;
+    return a;
+}
+}  // namespace
+extern "C" int tts_k_attention_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* lse,
+                                   const int32_t* klens, void* dQ, void* dK, void* dV, float* scratch, int B, int H, int Lq, int Lk,
+                                   int causal, void* stream) {
+    if (!Q || !K || !V || !O || !dO || !lse || !dQ || !dK || !dV || !scratch || B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return TTS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ld = H * 64;
+    const long nq = (long)B * Lq * ld;
+    float* dq32 = scratch; float* dsum = scratch + nq;
+    AttnParams f = ap_packed((const bf16*)Q, ld, (const bf16*)K, ld, (const bf16*)V, ld, (bf16*)const_cast<void*>(O), ld, B, Lq, Lk, klens, causal);
+    f.H = H;
+    cudaError_t e = cudaMemsetAsync(dq32, 0, nq * 4, st);
+    if (e != cudaSuccess) return (int)e;
+    attn_dsum_kernel<<<(B * H * Lq + 31) / 32, 256, 0, st>>>((const bf16*)O, (const bf16*)dO, f.o_bs, f.o_hs, f.o_rs, dsum, B, H, Lq);
+    ++launch_counter();
+    AttnBwdParams a = abp_packed(f, (const bf16*)dO, lse, dsum, dq32, ld, (bf16*)dK, ld, (bf16*)dV, ld);
+    e = launch_flash_attn_bwd_tc(a, st);
+    if (e != cudaSuccess) return (int)e;
+    f32_to_bf16_kernel<<<(unsigned)((nq / 4 + 255) / 256), 256, 0, st>>>(dq32, (bf16*)dQ, nq / 4);
+    ++launch_counter();
+    return (int)cudaGetLastError();
 }
 extern "C" int tts_k_layernorm(const float* X, const float* gamma, const float* beta, void* Y, int M, float eps, void* stream) {
     if (!X || !gamma || !beta || !Y || M <= 0) return TTS_E_ARG;

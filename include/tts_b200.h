@@ -108,6 +108,33 @@ int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* 
  * after every phase; this copies [n_steps][n_phases] stamps (ns) to the host and returns n_phases. [sync] */
 int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long long* out, int n_steps, void* stream);
 
+/* ---- training step (oracle: TransformerTTS.forward in .train() mode + tts_loss + autograd + torch.optim.Adam;
+ *      oracle/transformer_tts.py:forward, :tts_loss, :masked_batchnorm) ---------------- */
+/* Build the training state from the weights loaded so far: one flat fp32 parameter buffer (+ gradients, Adam
+ * moments), BatchNorm running statistics, bf16 operand copies.  [sync] */
+int tts_train_begin(TtsHandle* h);
+int tts_train_end(TtsHandle* h);
+size_t tts_train_workspace_bytes(TtsHandle* h, int B, int S, int T);
+/* Train-mode forward (batch-statistics BatchNorm, Philox dropout at every site), loss, full backward.  All pointers
+ * are DEVICE pointers.  Afterwards the gradient of every parameter is in the flat gradient buffer (tts_train_grads),
+ * loss_out[0] holds the scalar loss, and BatchNorm running statistics have been updated. */
+int tts_train_step(TtsHandle* h, void* workspace, const int64_t* phonemes, const int32_t* phoneme_lens, const float* mels,
+                   const int32_t* mel_lens, int B, int S, int T, uint64_t seed, int utt_offset, double p_residual,
+                   float pos_weight, float* loss_out, void* stream);
+/* Forward outputs of the last tts_train_step ([B][T][80], [B][T][80], [B][T] fp32, device pointers, any may be null). */
+int tts_train_outputs(TtsHandle* h, void* workspace, int B, int S, int T, float* mel_before, float* mel_after,
+                      float* stop_logits, void* stream);
+/* The flat fp32 gradient buffer (device pointer, numel): the data-parallel exchange is ONE all-reduce over it. */
+int tts_train_grads(TtsHandle* h, float** grads_dev, int64_t* numel);
+/* Adam over the flat buffers (g <- grad * grad_scale, e.g. 1 / world_size after a sum all-reduce), then refresh the
+ * bf16 operand copies. */
+int tts_train_adam(TtsHandle* h, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* Enumerate the tensors inside the flat buffers: state_dict name, offset, numel; is_buffer = 1 for running stats. */
+int tts_train_num_tensors(TtsHandle* h);
+int tts_train_tensor_info(TtsHandle* h, int index, const char** name, int64_t* offset, int64_t* numel, int* is_buffer);
+/* Copy a range of the parameter (which = 0), gradient (1) or running-statistics (2) buffer to the host. [sync] */
+int tts_train_read(TtsHandle* h, int which, int64_t offset, int64_t numel, float* host_out);
+
 /* ---- per-kernel entry points (tests/test_gpu_kernels.py; not part of the drop-in surface) ---- */
 /* C[M][N] = act(A[M][K] . W[N][K]^T + bias) ; bf16 in, fp32 out; act 0 none / 1 relu / 2 tanh (tcgen05 kernel, gemm_tc.cuh). */
 int tts_k_gemm(const void* A_bf16, const void* W_bf16, const float* bias, float* C, int M, int N, int K, int act, void* stream);

@@ -39,6 +39,16 @@ SIGNATURES = {
     "tts_infer_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _U64, _I, _P, _P, _P, C.POINTER(_I), _P]),
     "tts_forward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _U64, _I, _P, _P, _P, _P]),
     "tts_debug_phase_timestamps": (_I, [_P, _P, _P, _I, _P]),
+    "tts_train_begin": (_I, [_P]),
+    "tts_train_end": (_I, [_P]),
+    "tts_train_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
+    "tts_train_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _U64, _I, C.c_double, C.c_float, _P, _P]),
+    "tts_train_outputs": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "tts_train_grads": (_I, [_P, C.POINTER(_P), C.POINTER(_I64)]),
+    "tts_train_adam": (_I, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
+    "tts_train_num_tensors": (_I, [_P]),
+    "tts_train_tensor_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I)]),
+    "tts_train_read": (_I, [_P, _I, _I64, _I64, _P]),
     "tts_k_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "tts_k_conv5": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "tts_k_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

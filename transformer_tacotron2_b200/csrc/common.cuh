@@ -129,4 +129,7 @@ TTS_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
 template <int N>
 TTS_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+TTS_D float to_f32(float x) { return x; }
+TTS_D float to_f32(bf16 x) { return __bfloat162float(x); }
+
 }  // namespace tts

@@ -1,5 +1,6 @@
 // Parameters and fused epilogue of the sequence-parallel GEMM / conv kernel (gemm_tc.cuh):
 //     C[M,N] = epi( sum_tap A[m + tap - pad, :] . W[tap][n, :] )
+// epi order: + bias, + alpha * pe, word dropout, + residual, activation, bit dropout, length mask
 // used by the encoder, the cross-K/V projection, the teacher-forced decoder and the postnet
 // (SURVEY.md 8(a) rows a3, a4, a10).  gemm_store is the scalar (pair-wise) form of the epilogue; the kernel uses
 // a 16-byte vectorised form of the same arithmetic where the output is a plain matrix.
@@ -23,8 +24,10 @@ struct GemmParams {
     int act;
     const bf16* resid_bf16; const float* resid_f32; int ldr;
     const float* pe; float alpha;    // + alpha * pe[t][n]   (pe row stride 512)
+    const float* alpha_ptr;          // if set, alpha is read from device memory (trainable scalar)
     const int* lens;                 // zero rows with t >= lens[b]
     int drop_site; uint64_t seed; int utt_offset;   // p = 0.5 bit dropout after the activation (site < 0: off)
+    int dropw_site; uint32_t dropw_thresh; float dropw_scale;   // word dropout (training, P12) of (acc + bias + alpha * pe), BEFORE the residual
     float* out_f32; bf16* out_bf16; int ldo;
     int scatter;                     // GemmScatter
     // SC_CROSS_KV: out_bf16 = cache [layers][2][B][H][S][64], N = layers * 1024, T = S
@@ -39,6 +42,18 @@ TTS_D void gemm_store(const GemmParams& p, int m, int n, float v0, float v1) {
     const bool has1 = (n + 1) < p.N;
     const int b = m / p.T, t = m - b * p.T;
     if (p.bias) { v0 += p.bias[n]; if (has1) v1 += p.bias[n + 1]; }
+    if (p.pe) {
+        const float alpha = p.alpha_ptr ? *p.alpha_ptr : p.alpha;
+        v0 += alpha * p.pe[(size_t)t * kDModel + n];
+        if (has1) v1 += alpha * p.pe[(size_t)t * kDModel + n + 1];
+    }
+    if (p.dropw_site >= 0) {                         // n even: words n % 4 and n % 4 + 1 of chunk n / 4
+        const uint4 w = philox4x32_10(make_uint4((uint32_t)p.dropw_site, (uint32_t)t, (uint32_t)(p.utt_offset + b), (uint32_t)(n >> 2)),
+                                      (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        const uint32_t w0 = (n & 2) ? w.z : w.x, w1 = (n & 2) ? w.w : w.y;
+        v0 = w0 >= p.dropw_thresh ? v0 * p.dropw_scale : 0.f;
+        v1 = w1 >= p.dropw_thresh ? v1 * p.dropw_scale : 0.f;
+    }
     if (p.resid_bf16) {
         v0 += __bfloat162float(p.resid_bf16[(size_t)m * p.ldr + n]);
         if (has1) v1 += __bfloat162float(p.resid_bf16[(size_t)m * p.ldr + n + 1]);
@@ -46,10 +61,6 @@ TTS_D void gemm_store(const GemmParams& p, int m, int n, float v0, float v1) {
     if (p.resid_f32) {
         v0 += p.resid_f32[(size_t)m * p.ldr + n];
         if (has1) v1 += p.resid_f32[(size_t)m * p.ldr + n + 1];
-    }
-    if (p.pe) {
-        v0 += p.alpha * p.pe[(size_t)t * kDModel + n];
-        if (has1) v1 += p.alpha * p.pe[(size_t)t * kDModel + n + 1];
     }
     if (p.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
     else if (p.act == ACT_TANH) { v0 = tanhf(v0); v1 = tanhf(v1); }

@@ -173,6 +173,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                             f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
                         }
                     }
+                    if (g.pe) {
+                        const float alpha = g.alpha_ptr ? *g.alpha_ptr : g.alpha;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 pv = __ldg(reinterpret_cast<const float4*>(g.pe + (size_t)tt * kDModel + nb0 + j));
+                            f[j] += alpha * pv.x; f[j + 1] += alpha * pv.y; f[j + 2] += alpha * pv.z; f[j + 3] += alpha * pv.w;
+                        }
+                    }
+                    if (g.dropw_site >= 0) {             // word dropout (P12): 4 consecutive columns = one Philox call
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const uint4 w4 = philox4x32_10(make_uint4((uint32_t)g.dropw_site, (uint32_t)tt, (uint32_t)(g.utt_offset + bb), (uint32_t)((nb0 + j) >> 2)),
+                                                           (uint32_t)g.seed, (uint32_t)(g.seed >> 32));
+                            f[j] = w4.x >= g.dropw_thresh ? f[j] * g.dropw_scale : 0.f;
+                            f[j + 1] = w4.y >= g.dropw_thresh ? f[j + 1] * g.dropw_scale : 0.f;
+                            f[j + 2] = w4.z >= g.dropw_thresh ? f[j + 2] * g.dropw_scale : 0.f;
+                            f[j + 3] = w4.w >= g.dropw_thresh ? f[j + 3] * g.dropw_scale : 0.f;
+                        }
+                    }
                     if (g.resid_bf16) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
@@ -187,13 +206,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                         for (int j = 0; j < 32; j += 4) {
                             const float4 rv = *reinterpret_cast<const float4*>(g.resid_f32 + (size_t)m * g.ldr + nb0 + j);
                             f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
-                        }
-                    }
-                    if (g.pe) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 pv = __ldg(reinterpret_cast<const float4*>(g.pe + (size_t)tt * kDModel + nb0 + j));
-                            f[j] += g.alpha * pv.x; f[j + 1] += g.alpha * pv.y; f[j + 2] += g.alpha * pv.z; f[j + 3] += g.alpha * pv.w;
                         }
                     }
                     if (g.act == ACT_RELU) {

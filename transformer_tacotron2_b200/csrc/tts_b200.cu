@@ -19,9 +19,11 @@
 #include "attention_bwd_tc.cuh"
 #include "misc_kernels.cuh"
 #include "decode_cluster.cuh"
+#include "train_kernels.cuh"
 
 using namespace tts;
 
+struct TtsTrain;
 // ------------------------------------------------------------------------------------------------
 struct TtsHandle {
     TtsConfig cfg;
@@ -53,6 +55,7 @@ struct TtsHandle {
     // ---- decode session
     bool dec_active = false; int dec_B = 0, dec_S = 0, dec_T = 0, dec_t = 0; uint64_t dec_seed = 0; int dec_utt0 = 0;
     int* h_status = nullptr;                                          // pinned: t_done, n_finished
+    TtsTrain* train = nullptr;                                        // training state (train.cuh), built by tts_train_begin
 };
 
 #define CK(call)                                                                                     \
@@ -126,12 +129,14 @@ extern "C" int tts_create(const TtsConfig* cfg, int device, TtsHandle** out) {
     return 0;
 }
 
+extern "C" int tts_train_end(TtsHandle* h);
 extern "C" int tts_destroy(TtsHandle* h) {
     if (!h) return TTS_E_ARG;
     cudaSetDevice(h->device);
     if (h->arena) cudaFree(h->arena);
     if (h->cl_wpack) cudaFree(h->cl_wpack);
     if (h->h_status) cudaFreeHost(h->h_status);
+    tts_train_end(h);
     delete h;
     return 0;
 }
@@ -379,8 +384,7 @@ extern "C" int tts_finalize_weights(TtsHandle* h) {
     CK(cudaMemcpy(h->arena, ar.host.data(), ar.host.size(), cudaMemcpyHostToDevice));
     for (auto& f : fixes) *f.dst = h->arena + f.off;
     CK(cudaDeviceSynchronize());
-    h->finalized = true;
-    h->staged.clear();
+    h->finalized = true;                                              // (the staged fp32 copies stay: tts_train_begin builds the master from them)
     return 0;
 }
 
@@ -395,7 +399,7 @@ namespace {
 GemmParams gp(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K) {
     GemmParams p; memset(&p, 0, sizeof(p));
     p.A = A; p.lda = lda; p.W = W; p.ldw = ldw; p.M = M; p.N = N; p.K = K; p.taps = 1; p.Nw = round_up(N, 128);
-    p.T = M; p.drop_site = -1; p.B = 1;
+    p.T = M; p.drop_site = -1; p.dropw_site = -1; p.B = 1;
     return p;
 }
 AttnParams ap_packed(const bf16* Q, int ldq, const bf16* K, int ldk, const bf16* V, int ldv, bf16* O, int ldo,
@@ -842,4 +846,88 @@ extern "C" int tts_k_philox_bits(uint64_t seed, int site, int T, int B, int C, i
     philox_bits_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seed, site, T, B, C, utt_offset, out);
     ++launch_counter();
     return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// training (train.cuh)
+#include "train.cuh"
+
+extern "C" int tts_train_begin(TtsHandle* h) {
+    if (!h) return TTS_E_ARG;
+    if (!h->finalized) FAIL(TTS_E_STATE, "weights not finalised");
+    CK(cudaSetDevice(h->device));
+    train_free(h);
+    int r = train_build(h);
+    if (r) { train_free(h); return r; }
+    if ((r = train_repack(h, 0))) return r;
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" int tts_train_end(TtsHandle* h) { if (!h) return TTS_E_ARG; cudaSetDevice(h->device); return train_free(h); }
+extern "C" size_t tts_train_workspace_bytes(TtsHandle* h, int B, int S, int T) {
+    if (!h || B <= 0 || S <= 0 || T <= 0) return 0;
+    return TrWs::make(nullptr, B, S, T).total;
+}
+extern "C" int tts_train_step(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* phoneme_lens, const float* mels, const int32_t* mel_lens,
+                              int B, int S, int T, uint64_t seed, int utt_offset, double p_residual, float pos_weight, float* loss_out, void* stream) {
+    if (!h || !ws || !phonemes || !phoneme_lens || !mels || !mel_lens || !loss_out || B <= 0 || S <= 0 || T <= 0) return TTS_E_ARG;
+    if (!h->train) FAIL(TTS_E_STATE, "tts_train_begin has not been called");
+    if (S > h->cfg.max_pos || T > h->cfg.max_pos) FAIL(TTS_E_ARG, "sequence exceeds max_pos");
+    if (p_residual < 0.0 || p_residual >= 1.0) FAIL(TTS_E_ARG, "p_residual out of range");
+    CK(cudaSetDevice(h->device));
+    TrCtx c;
+    c.h = h; c.t = h->train; c.w = TrWs::make(reinterpret_cast<unsigned char*>(ws), B, S, T); c.st = (cudaStream_t)stream;
+    c.B = B; c.S = S; c.T = T; c.seed = seed; c.utt0 = utt_offset;
+    c.thresh = (uint32_t)(p_residual * 4294967296.0); c.dscale = 1.0f / (float)(1.0 - p_residual);
+    c.P = h->train->P; c.G = h->train->G;
+    CK(cudaMemcpyAsync(c.w.plens, phoneme_lens, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
+    CK(cudaMemcpyAsync(c.w.mlens, mel_lens, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
+    return train_forward_backward(c, phonemes, mels, loss_out, pos_weight);
+}
+extern "C" int tts_train_outputs(TtsHandle* h, void* ws, int B, int S, int T, float* mel_before, float* mel_after, float* stop_logits, void* stream) {
+    if (!h || !ws || !h->train) return TTS_E_ARG;
+    TrWs w = TrWs::make(reinterpret_cast<unsigned char*>(ws), B, S, T);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mel_before) CK(cudaMemcpyAsync(mel_before, w.mel_before, (size_t)B * T * 80 * 4, cudaMemcpyDeviceToDevice, st));
+    if (mel_after) CK(cudaMemcpyAsync(mel_after, w.mel_after, (size_t)B * T * 80 * 4, cudaMemcpyDeviceToDevice, st));
+    if (stop_logits) CK(cudaMemcpyAsync(stop_logits, w.stop, (size_t)B * T * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+extern "C" int tts_train_grads(TtsHandle* h, float** grads_dev, int64_t* numel) {
+    if (!h || !h->train || !grads_dev || !numel) return TTS_E_ARG;
+    *grads_dev = h->train->G; *numel = (int64_t)h->train->n;
+    return 0;
+}
+extern "C" int tts_train_adam(TtsHandle* h, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+    if (!h || !h->train) return TTS_E_ARG;
+    CK(cudaSetDevice(h->device));
+    TtsTrain* t = h->train;
+    cudaStream_t st = (cudaStream_t)stream;
+    ++t->step;
+    const float bc1 = 1.f - std::pow(beta1, (float)t->step), bc2 = 1.f - std::pow(beta2, (float)t->step);
+    adam_kernel<<<1184, 256, 0, st>>>(t->P, t->G, t->M1, t->V2, (long)t->n, lr, beta1, beta2, eps, bc1, bc2, grad_scale);
+    ++launch_counter();
+    CK(cudaGetLastError());
+    return train_repack(h, st);
+}
+extern "C" int tts_train_num_tensors(TtsHandle* h) { return (h && h->train) ? (int)(h->train->params.size() + h->train->buffers.size()) : -1; }
+extern "C" int tts_train_tensor_info(TtsHandle* h, int index, const char** name, int64_t* offset, int64_t* numel, int* is_buffer) {
+    if (!h || !h->train || !name || !offset || !numel || !is_buffer || index < 0) return TTS_E_ARG;
+    TtsTrain* t = h->train;
+    const int np = (int)t->params.size();
+    if (index >= np + (int)t->buffers.size()) return TTS_E_ARG;
+    const TrEntry& e = index < np ? t->params[index] : t->buffers[index - np];
+    *name = e.name.c_str(); *offset = (int64_t)e.off; *numel = (int64_t)e.numel; *is_buffer = index >= np;
+    return 0;
+}
+extern "C" int tts_train_read(TtsHandle* h, int which, int64_t offset, int64_t numel, float* host_out) {
+    if (!h || !h->train || !host_out || offset < 0 || numel <= 0) return TTS_E_ARG;
+    TtsTrain* t = h->train;
+    const float* src = which == 0 ? t->P : which == 1 ? t->G : which == 2 ? t->RS : nullptr;
+    const size_t lim = which == 2 ? t->nrs : t->n;
+    if (!src || (size_t)(offset + numel) > lim) return TTS_E_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host_out, src + offset, (size_t)numel * 4, cudaMemcpyDeviceToHost));
+    return 0;
 }

@@ -1,0 +1,122 @@
+"""Training step of the B200 path: the counterpart of
+
+    model.train(); out = model(ph, pl, mels, ml, seed); loss = tts_loss(*out, mels, ml); loss.backward()
+    (all-reduce of the gradients across data-parallel ranks); torch.optim.Adam(...).step()
+
+on the oracle (oracle/transformer_tts.py: TransformerTTS.forward, tts_loss).  All arithmetic runs in libtts_b200.so
+(tts_train_* in include/tts_b200.h); torch is used for device memory and for the data-parallel all-reduce over the
+library's single flat gradient buffer (NCCL on GPUs; SURVEY.md 8(e): one exchange step, per-rank BatchNorm statistics)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .model import TransformerTTS
+
+
+class _DevBuf:
+    """A device range exposed through __cuda_array_interface__ so that torch can wrap it without copying."""
+
+    def __init__(self, ptr: int, numel: int):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+
+class Trainer:
+    def __init__(self, model: TransformerTTS, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.98), eps: float = 1e-9,
+                 p_residual: float = 0.1, pos_weight: float = 5.0, process_group=None, world_size: int = 1):
+        self.model = model
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.p_residual, self.pos_weight = float(p_residual), float(pos_weight)
+        self.group, self.world_size = process_group, int(world_size)
+        lib = model._ensure_handle()
+        model.sync_weights()
+        model._check(lib.tts_train_begin(model._handle), "tts_train_begin")
+        self._lib, self._h = lib, model._handle
+        ptr, n = C.c_void_p(), C.c_int64()
+        model._check(lib.tts_train_grads(self._h, C.byref(ptr), C.byref(n)), "tts_train_grads")
+        self.flat_grads = torch.as_tensor(_DevBuf(ptr.value, n.value), device=model.device)      # view, no copy
+        self._loss = torch.zeros(1, device=model.device)
+        self._ws, self._ws_key = None, None
+        self._table = []
+        name, off, numel, isb = C.c_char_p(), C.c_int64(), C.c_int64(), C.c_int()
+        for i in range(lib.tts_train_num_tensors(self._h)):
+            model._check(lib.tts_train_tensor_info(self._h, i, C.byref(name), C.byref(off), C.byref(numel), C.byref(isb)), "tts_train_tensor_info")
+            self._table.append((name.value.decode(), off.value, numel.value, bool(isb.value)))
+
+    # ------------------------------------------------------------------ one step
+    def _workspace(self, B, S, T):
+        if self._ws_key != (B, S, T):
+            n = self._lib.tts_train_workspace_bytes(self._h, B, S, T)
+            self._ws = None
+            self._ws = torch.empty(n, dtype=torch.uint8, device=self.model.device)
+            self._ws_key = (B, S, T)
+        return self._ws
+
+    def forward_backward(self, phonemes, phoneme_lens, mels, mel_lens, seed: int = 0, utt_offset: int = 0) -> torch.Tensor:
+        """Train-mode forward + loss + backward.  Returns the loss (1-element device tensor); gradients are in flat_grads."""
+        m, dev = self.model, self.model.device
+        B, S = phonemes.shape
+        T = mels.shape[1]
+        self._in = (phonemes.to(dev, torch.int64).contiguous(), phoneme_lens.to(dev, torch.int32).contiguous(),
+                    mels.to(dev, torch.float32).contiguous(), mel_lens.to(dev, torch.int32).contiguous())
+        ph, pl, me, ml = self._in
+        ws = self._workspace(B, S, T)
+        rc = self._lib.tts_train_step(self._h, ws.data_ptr(), ph.data_ptr(), pl.data_ptr(), me.data_ptr(), ml.data_ptr(), B, S, T, int(seed),
+                                      int(utt_offset), self.p_residual, self.pos_weight, self._loss.data_ptr(), m._stream())
+        m._check(rc, "tts_train_step")
+        self._shape = (B, S, T)
+        return self._loss
+
+    def all_reduce_grads(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+
+    def adam_step(self):
+        rc = self._lib.tts_train_adam(self._h, self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world_size, self.model._stream())
+        self.model._check(rc, "tts_train_adam")
+        self.model._dirty = True          # the module's host copies are stale until export_to_module()
+
+    def step(self, phonemes, phoneme_lens, mels, mel_lens, seed: int = 0, utt_offset: int = 0) -> torch.Tensor:
+        loss = self.forward_backward(phonemes, phoneme_lens, mels, mel_lens, seed, utt_offset)
+        self.all_reduce_grads()
+        self.adam_step()
+        return loss
+
+    # ------------------------------------------------------------------ inspection
+    def outputs(self):
+        B, S, T = self._shape
+        dev = self.model.device
+        mb, ma, st = torch.empty(B, T, 80, device=dev), torch.empty(B, T, 80, device=dev), torch.empty(B, T, device=dev)
+        rc = self._lib.tts_train_outputs(self._h, self._ws.data_ptr(), B, S, T, mb.data_ptr(), ma.data_ptr(), st.data_ptr(), self.model._stream())
+        self.model._check(rc, "tts_train_outputs")
+        return mb, ma, st
+
+    def _read(self, which: int) -> Dict[str, torch.Tensor]:
+        shapes = {k: v.shape for k, v in self.model.state_dict().items()}
+        out = {}
+        for name, off, numel, isb in self._table:
+            if isb != (which == 2):
+                continue
+            t = torch.empty(numel, dtype=torch.float32)
+            self.model._check(self._lib.tts_train_read(self._h, which, off, numel, C.c_void_p(t.data_ptr())), "tts_train_read")
+            out[name] = t.view(shapes[name])
+        return out
+
+    def grads(self) -> Dict[str, torch.Tensor]:
+        return self._read(1)
+
+    def parameters(self) -> Dict[str, torch.Tensor]:
+        return self._read(0)
+
+    def buffers(self) -> Dict[str, torch.Tensor]:
+        return self._read(2)
+
+    def export_to_module(self):
+        """Copy the trained parameters and BatchNorm statistics back into the nn.Module (for inference / state_dict())."""
+        sd = self.model.state_dict()
+        for k, v in {**self.parameters(), **self.buffers()}.items():
+            sd[k].copy_(v)
+        self.model._dirty = True

@@ -65,14 +65,13 @@ struct TrWs {
     float *acc, *dbefore, *dafter, *dstop;
     // backward scratch
     float *dx, *dxa, *dq32, *dsum;
-    bf16 *dsub, *dwide, *dqkv, *dctx, *dkv, *dhead, *At, *Bt, *dcv, *dcv2;
+    bf16 *dsub, *dwide, *dqkv, *dctx, *dkv, *dhead, *dcv, *dcv2;
     int *plens, *mlens;
     static TrWs make(unsigned char* base, int B, int S, int T) {
         TrWs w; size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return base + r; };
         const size_t Me = (size_t)B * S, Md = (size_t)B * T, Mx = Me > Md ? Me : Md;
         w.Mep = (int)((Me + 63) / 64 * 64); w.Mdp = (int)((Md + 63) / 64 * 64);
-        const size_t Mxp = w.Mep > w.Mdp ? w.Mep : w.Mdp;
         for (auto& p : w.e) p = (bf16*)take(Me * 512 * 2);
         for (auto& p : w.ec) p = (float*)take(Me * 512 * 4);
         for (auto& p : w.xe) p = (bf16*)take(Me * 512 * 2);
@@ -99,7 +98,6 @@ struct TrWs {
         w.dx = (float*)take(Mx * 512 * 4); w.dxa = (float*)take(Mx * 512 * 4); w.dq32 = (float*)take(Mx * 512 * 4); w.dsum = (float*)take(Mx * 8 * 4);
         w.dsub = (bf16*)take(Mx * 512 * 2); w.dwide = (bf16*)take(Mx * 2048 * 2); w.dqkv = (bf16*)take(Mx * 1536 * 2); w.dctx = (bf16*)take(Mx * 512 * 2);
         w.dkv = (bf16*)take(Me * 6144 * 2); w.dhead = (bf16*)take(Md * 128 * 2);
-        w.At = (bf16*)take((size_t)6144 * Mxp * 2); w.Bt = (bf16*)take((size_t)2560 * Mxp * 2);
         w.dcv = (bf16*)take(Mx * 512 * 2); w.dcv2 = (bf16*)take(Mx * 512 * 2);
         w.plens = (int*)take((size_t)B * 4); w.mlens = (int*)take((size_t)B * 4);
         w.total = o;
@@ -246,22 +244,14 @@ GemmParams tr_dgrad(TrCtx& c, const bf16* dY, int ldy, int Kdy, int M, int Trows
     p.Nw = m.Kw; p.taps = m.taps; p.T = Trows; p.B = M / Trows;
     return p;
 }
-// weight gradient dW[N][K * taps] = sum_m dY[m][n] X[m + tap - pad][k] (+ bias gradient), written into G
+// weight gradient dW[N][K * taps] += sum_m dY[m][n] X[m + tap - pad][k] (+ bias gradient), accumulated into G (wgrad_tc.cuh)
 int tr_wgrad(TrCtx& c, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int Trows, int mat, size_t bias_off, bool has_bias = true) {
     const TrMat& m = c.t->mats[mat];
-    const int Mp = (M + 63) / 64 * 64;
-    dim3 blk(32, 8);
-    transpose_shift_kernel<<<dim3((Mp + 31) / 32, (m.N + 31) / 32, 1), blk, 0, c.st>>>(dY, ldy, c.w.At, m.N, Trows, M, Mp, 1);
-    transpose_shift_kernel<<<dim3((Mp + 31) / 32, (m.K + 31) / 32, m.taps), blk, 0, c.st>>>(X, ldx, c.w.Bt, m.K, Trows, M, Mp, m.taps);
-    launch_counter() += 2;
-    GemmParams p = gp(c.w.At, Mp, c.w.Bt, Mp, m.N, m.K * m.taps, Mp);
-    p.out_f32 = c.G + m.off; p.ldo = m.K * m.taps;
-    TRL(launch_gemm_tc(p, c.st));
-    if (has_bias) {
-        colsum_kernel<bf16><<<dim3((m.N + 127) / 128, 64), 128, 0, c.st>>>(dY, ldy, M, m.N, c.G + bias_off);
-        ++launch_counter();
-    }
-    TRL(cudaGetLastError());
+    WgradParams g;
+    g.dY = dY; g.ldy = ldy; g.Cout = m.N; g.X = X; g.ldx = ldx; g.Cin = m.K; g.taps = m.taps;
+    g.T = m.taps > 1 ? Trows : M; g.nb = M / g.T;
+    g.dW = c.G + m.off; g.dbias = has_bias ? c.G + bias_off : nullptr;
+    TRL(launch_wgrad_tc(g, c.st));
     return 0;
 }
 int tr_ln_bwd(TrCtx& c, const float* dx, const float* ypre, size_t g_off, size_t b_off, int M, int Trows, int site, float* dy32, bf16* dsub) {

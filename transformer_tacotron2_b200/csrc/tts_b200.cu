@@ -20,6 +20,7 @@
 #include "misc_kernels.cuh"
 #include "decode_cluster.cuh"
 #include "train_kernels.cuh"
+#include "wgrad_tc.cuh"
 
 using namespace tts;
 

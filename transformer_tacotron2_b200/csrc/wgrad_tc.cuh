@@ -1,0 +1,229 @@
+// Weight-gradient GEMM on tcgen05 / TMEM / TMA (training path):
+//     dW[n][k * taps + tap] += sum_{b, t} dY[b, t, n] * X[b, t + tap - pad, k]          (the reduction runs over TOKENS)
+// Both operands are read straight from the row-major activations [tokens][features] as MN-major UMMA operands (the feature
+// dimension is contiguous, the reduction dimension is the row index): TMA boxes {64 features, 64 tokens} with 128B swizzle,
+// two boxes per 128-wide operand tile (LBO = 8 KB between them) -- no transposed copies of dY or X are ever made.  The
+// conv taps shift the token coordinate of X inside the utterance's own 3-D slice (TMA zero-fills outside), as in gemm_tc.cuh.
+// The output is tiny (<= 6144 x 512) while the reduction is long (25.6k-51.2k tokens), so every output tile is split along
+// the token axis (split-K) to fill the 148 SMs; partial tiles are added with red.global.add.f32 into the zeroed gradient
+// buffer.  Persistent CTAs, 192 threads (TMA warp / MMA warp / 4 epilogue warps), double-buffered TMEM accumulator.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "attention_bwd_tc.cuh"     // fb_desc_mn
+
+namespace tts {
+
+struct WgradParams {
+    const bf16* dY; int ldy; int Cout;
+    const bf16* X; int ldx; int Cin;
+    int taps, T, nb;                  // rows per utterance, utterances (M = nb * T)
+    float* dW;                        // [Cout][Cin * taps] fp32, accumulated
+    float* dbias;                     // optional [Cout]: += column sums of dY (added by the n-tile 0 / tap 0 items)
+};
+
+struct WgradTcParams {
+    alignas(64) CUtensorMap tm_dy, tm_x;     // bf16 {C, T, nb}, box {64, 64, 1}, SWIZZLE_128B
+    WgradParams g;
+    int tiles_m, tiles_n, n_tiles;           // output tiles: Cout/128 x Cin/128 x taps
+    int kb_per_utt, n_kb, splits, kb_per_split, n_items;
+};
+
+constexpr int WG_STAGES = 4, WG_STAGE_BYTES = 32768, WG_THREADS = 192;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 256;
+constexpr uint32_t WG_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
+    extern __shared__ __align__(1024) unsigned char wg_smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(wg_smem + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* empty = full + WG_STAGES;
+    uint64_t* tmem_full = empty + WG_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WgradParams& g = p.g;
+    const int pad = g.taps >> 1;
+
+    if (threadIdx.x == 0) {
+        if (tc_smem_u32(wg_smem) & 1023) __trap();
+        for (int s = 0; s < WG_STAGES; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // item -> (tile, split); tile -> (mt, nt, tap); split -> token blocks [kb0, kb1)
+    if (warp == 0) {
+        if (lane == 0) {                                 // ---------------- TMA producer
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int tile = item / p.splits, sp = item - tile * p.splits;
+                const int tap = tile % g.taps, nt = (tile / g.taps) % p.tiles_n, mt = tile / (g.taps * p.tiles_n);
+                const int kb0 = sp * p.kb_per_split, kb1 = min(p.n_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % WG_STAGES; const uint32_t use = it / WG_STAGES;
+                    if (use > 0) tc_mbar_wait(&empty[s], (use & 1) ^ 1);
+                    const int b = kb / p.kb_per_utt, t0 = (kb - b * p.kb_per_utt) * 64;
+                    unsigned char* dst = wg_smem + s * WG_STAGE_BYTES;
+                    tc_mbar_expect_tx(&full[s], WG_STAGE_BYTES);
+                    tc_tma_3d(dst, &p.tm_dy, mt * 128, t0, b, &full[s]);
+                    tc_tma_3d(dst + 8192, &p.tm_dy, mt * 128 + 64, t0, b, &full[s]);
+                    tc_tma_3d(dst + 16384, &p.tm_x, nt * 128, t0 + tap - pad, b, &full[s]);
+                    tc_tma_3d(dst + 24576, &p.tm_x, nt * 128 + 64, t0 + tap - pad, b, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                 // ---------------- MMA issuer
+            uint32_t it = 0, j = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
+                const int sp = item % p.splits;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(p.n_kb, kb0 + p.kb_per_split);
+                const uint32_t acc = j & 1, ause = j >> 1;
+                if (ause > 0) tc_mbar_wait(&tmem_empty[acc], (ause & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + acc * 128;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % WG_STAGES; const uint32_t use = it / WG_STAGES;
+                    tc_mbar_wait(&full[s], use & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = tc_smem_u32(wg_smem + s * WG_STAGE_BYTES), b_addr = a_addr + 16384;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)          // 16 tokens per MMA = 16 rows x 128 B inside each box
+                        ft_mma(d_tmem, fb_desc_mn(a_addr + k * 2048, 8192), fb_desc_mn(b_addr + k * 2048, 8192), WG_IDESC, (kb > kb0) || k != 0);
+                    ft_commit(&empty[s]);
+                }
+                ft_commit(&tmem_full[acc]);
+            }
+        }
+    } else {                                             // ---------------- epilogue: thread = output row n (a dY feature)
+        const int lg = warp & 3;
+        uint32_t j = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
+            const int tile = item / p.splits, sp = item - tile * p.splits;
+            const int tap = tile % g.taps, nt = (tile / g.taps) % p.tiles_n, mt = tile / (g.taps * p.tiles_n);
+            const int kb0 = sp * p.kb_per_split;
+            const uint32_t acc = j & 1;
+            const bool nonempty = kb0 < p.n_kb;
+            if (nonempty) {
+                tc_mbar_wait(&tmem_full[acc], (j >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const int n = mt * 128 + lg * 32 + lane;
+            const int ldo = g.Cin * g.taps;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t v[32];
+                if (nonempty) {
+                    ft_ld32_nowait(tmem_base + acc * 128 + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+                    ft_ld_wait();
+                    if (n < g.Cout) {
+                        const int kcol = nt * 128 + c0;
+                        float* o = g.dW + (size_t)n * ldo;
+                        if (g.taps == 1 && kcol + 32 <= g.Cin && (ldo & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4)
+                                fb_red4(o + kcol + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (kcol + i < g.Cin) atomicAdd(o + (size_t)(kcol + i) * g.taps + tap, __uint_as_float(v[i]));
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && nonempty) ft_arrive(&tmem_empty[acc]);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
+// dbias[c] += sum_m x[m][c] : 8 columns per thread (16-byte loads); a block covers cpb column groups x (256 / cpb) row lanes,
+// rows strided over the grid; row lanes are summed in shared memory before the atomics
+__global__ void __launch_bounds__(256) colsum8_kernel(const bf16* __restrict__ x, int ld, int M, int C8, int cpb, float* __restrict__ out) {
+    __shared__ float red[256 * 8];
+    const int rl = 256 / cpb, cl = threadIdx.x % cpb, rlane = threadIdx.x / cpb;
+    const int cg = blockIdx.y * cpb + cl;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (cg < C8 && rlane < rl)
+        for (int m = blockIdx.x * rl + rlane; m < M; m += gridDim.x * rl) {
+            const uint4 v = *reinterpret_cast<const uint4*>(x + (size_t)m * ld + cg * 8);
+            const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+        }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+    __syncthreads();
+    if (rlane == 0 && cg < C8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float t = 0.f;
+            for (int r = 0; r < rl; ++r) t += red[(r * cpb + cl) * 8 + i];
+            atomicAdd(out + cg * 8 + i, t);
+        }
+    }
+}
+
+inline cudaError_t launch_wgrad_tc(const WgradParams& g, cudaStream_t stream) {
+    static bool attr_set = false;
+    static int num_sms = 0;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_set = true;
+    }
+    TcEncodeFn enc = tc_encode_fn();
+    if (!enc || (g.ldy & 7) || (g.ldx & 7)) return cudaErrorInvalidValue;
+    WgradTcParams p;
+    p.g = g;
+    auto make = [&](CUtensorMap* tm, const bf16* base, int C, int ld) -> bool {
+        const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)g.T, (cuuint64_t)g.nb};
+        const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * g.T};
+        const cuuint32_t box[3] = {64, 64, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (!make(&p.tm_dy, g.dY, g.Cout, g.ldy) || !make(&p.tm_x, g.X, g.Cin, g.ldx)) return cudaErrorInvalidValue;
+    p.tiles_m = (g.Cout + 127) / 128; p.tiles_n = (g.Cin + 127) / 128;
+    p.n_tiles = p.tiles_m * p.tiles_n * g.taps;
+    p.kb_per_utt = (g.T + 63) / 64; p.n_kb = p.kb_per_utt * g.nb;
+    int splits = (2 * num_sms + p.n_tiles - 1) / p.n_tiles;              // ~2 work items per SM
+    splits = std::max(1, std::min(splits, (p.n_kb + 3) / 4));            // at least 4 token blocks per item
+    p.kb_per_split = (p.n_kb + splits - 1) / splits;
+    p.splits = (p.n_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.n_items = p.n_tiles * p.splits;
+    const int grid = std::min(p.n_items, num_sms);
+    wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(p);
+    ++launch_counter();
+    if (g.dbias) {
+        const int M = g.T * g.nb;
+        if ((g.Cout & 7) == 0) {
+            const int C8 = g.Cout / 8, cpb = std::min(C8, 256);
+            colsum8_kernel<<<dim3(num_sms, (C8 + cpb - 1) / cpb), 256, 0, stream>>>(g.dY, g.ldy, M, C8, cpb, g.dbias);
+        } else {
+            colsum_kernel<bf16><<<dim3((g.Cout + 127) / 128, 256), 128, 0, stream>>>(g.dY, g.ldy, M, g.Cout, g.dbias);
+        }
+        ++launch_counter();
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace tts

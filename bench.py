@@ -16,7 +16,9 @@ collective (weak scaling: 64 utterances per GPU; `--scaling strong` splits a fix
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs already in HBM, CUDA-event
 timed); `e2e` = the same through TransformerTTS.inference with HOST tensors (H2D + D2H inside the timed
 region); `roofline` = the persistent decode kernel's algorithmic HBM bytes / its CUDA-event duration
-against the measured copy bandwidth; `cpu_baseline` = the oracle on the box's host cores (bounded sample).
+against the measured copy bandwidth; `cpu_baseline` = the oracle on the box's host cores (bounded sample);
+`train` = the other half of BASELINE.json's metric: utterances/s of the full train step (configs[3], B = 32 per GPU,
+data parallel with one all-reduce over the flat gradient buffer), same timing rules.
 """
 from __future__ import annotations
 
@@ -256,6 +258,34 @@ def run_b200(args, rank, world, local_rank):
     h2d = B * S * 8 + B * 4
     d2h = B * T * 80 * 4 + B * T * 4 + B * 4
 
+    # ---- second half of BASELINE.json's metric: teacher-forced train step (configs[3]: B = 32 per GPU, data parallel,
+    #      one NCCL all-reduce over the flat gradient buffer per step), utterances / s over all ranks -------------------
+    train = None
+    if not args.no_train:
+        from transformer_tacotron2_b200.training import Trainer
+        Bt, Tt = args.train_batch, T
+        tr = Trainer(model, lr=1e-4, world_size=world)
+        g = torch.Generator().manual_seed(DATA_SEED + 1000 + rank)
+        tph = torch.randint(1, 128, (Bt, S), generator=g).to(dev); tpl = torch.full((Bt,), S, dtype=torch.int32, device=dev)
+        tmel = torch.randn(Bt, Tt, 80, generator=g).clamp(-4, 4).to(dev); tml = torch.full((Bt,), Tt, dtype=torch.int32, device=dev)
+        for i in range(args.warmup):
+            tr.step(tph, tpl, tmel, tml, seed=DROPOUT_SEED + i, utt_offset=rank * Bt)
+        barrier()
+        launches_t0 = lib.tts_launch_count()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for i in range(args.steps):
+            loss = tr.step(tph, tpl, tmel, tml, seed=DROPOUT_SEED + 100 + i, utt_offset=rank * Bt)
+        t1e.record()
+        barrier()
+        train_ms = max_over_ranks(t0e.elapsed_time(t1e)) / args.steps
+        train = {"metric": "utterances/s, teacher-forced train step (forward + loss + backward + all-reduce + Adam)",
+                 "value": world * Bt / (train_ms * 1e-3), "unit": "utt/s", "ms_per_step": train_ms, "loss": float(loss),
+                 "gpu_launches_per_step": int((lib.tts_launch_count() - launches_t0) // args.steps),
+                 "config": {"workload": f"configs[3]: base model train step, B={Bt}/GPU, S={S}, T={Tt}, bf16 operands / fp32 accumulate, "
+                                        f"fp32 master + Adam, data parallel x{world} (one NCCL all-reduce over 53.0 M fp32 gradients)"}}
+        tr = None
+
     if rank != 0:
         return
     peak, peak_kind = measured_peaks()
@@ -285,6 +315,8 @@ def run_b200(args, rank, world, local_rank):
                      "kernel_ms_per_launch": dec_ms, "us_per_decoder_step": 1e3 * dec_ms / T},
         "clocks": clocks,
     }
+    if train is not None:
+        line["train"] = train
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, desc = cpu_oracle_sample(B, S, T, window=args.cpu_window, threads=threads)
@@ -307,6 +339,8 @@ def main():
     ap.add_argument("--cpu-window", type=int, default=50)
     ap.add_argument("--ref-window", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step measurement (the `train` key)")
+    ap.add_argument("--train-batch", type=int, default=32)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -108,3 +108,30 @@ def test_loss_decreases_over_steps(oracle_model):
     losses = [float(tr.step(*inputs, seed=100 + i)) for i in range(12)]
     assert all(l == l for l in losses)
     assert min(losses[-3:]) < 0.9 * losses[0], losses        # (a new dropout mask every step: noisy, but clearly down)
+
+
+def test_data_parallel_shards_match_oracle(oracle_model):
+    """Two data-parallel 'ranks' run one after the other on this GPU (utt_offset = first global utterance id of the shard):
+    the mean of their flat gradients equals the mean of the oracle's per-shard gradients (per-rank BatchNorm statistics,
+    dropout masks keyed by the global utterance id -- SURVEY.md 8(e))."""
+    from oracle import synthetic
+    from oracle.transformer_tts import tts_loss
+    from transformer_tacotron2_b200.training import Trainer
+    ph, pl, mels, ml = synthetic.make_inputs(4, 16, 40, 31, True)
+    tr = Trainer(make_b200_model(oracle_model))
+    got, want = None, None
+    for lo, hi in ((0, 2), (2, 4)):
+        tr.forward_backward(ph[lo:hi], pl[lo:hi], mels[lo:hi], ml[lo:hi], seed=9, utt_offset=lo)
+        g = tr.flat_grads.clone()
+        got = g if got is None else got + g
+        m = copy.deepcopy(oracle_model).train()
+        out = m(ph[lo:hi], pl[lo:hi], mels[lo:hi], ml[lo:hi], seed=9, utt_ids=list(range(lo, hi)))
+        tts_loss(*out, mels[lo:hi], ml[lo:hi]).backward()
+        ref = {k: p.grad for k, p in m.named_parameters()}
+        flat = torch.zeros_like(g, device="cpu")
+        for name, off, numel, isb in tr._table:
+            if not isb:
+                flat[off:off + numel] = ref[name].flatten()
+        want = flat if want is None else want + flat
+    err = rel_l2(got / 2, want / 2)
+    assert err < TOL_GRAD_ALL, err

@@ -48,6 +48,45 @@ def test_sharded_inference_world2_gloo(tmp_path):
     assert open(out).read() == "ok"
 
 
+def _dp_worker(rank, world, port, out_path):
+    """Data-parallel training exchange: each rank differentiates its own shard (per-rank BatchNorm
+    statistics, dropout masks keyed by the GLOBAL utterance id), ONE all-reduce over the flat gradient, mean = sum / world."""
+    import copy
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from oracle import synthetic
+    from oracle.transformer_tts import tts_loss
+    from transformer_tacotron2_b200.sharding import shard_range
+    from transformer_tacotron2_b200.training import allreduce_sum_
+    base = synthetic.make_model(stop_bias=-8.0)
+    ph, pl, mels, ml = synthetic.make_inputs(4, 6, 8, 17, ragged=True)
+
+    def shard_grads(r):
+        lo, hi = shard_range(4, world, r)
+        m = copy.deepcopy(base).train()
+        out = m(ph[lo:hi], pl[lo:hi], mels[lo:hi], ml[lo:hi], seed=5, utt_ids=list(range(lo, hi)))
+        tts_loss(*out, mels[lo:hi], ml[lo:hi]).backward()
+        return torch.cat([p.grad.flatten() for p in m.parameters()])
+
+    flat = shard_grads(rank)
+    allreduce_sum_(flat)
+    flat /= world
+    if rank == 0:
+        want = sum(shard_grads(r) for r in range(world)) / world
+        ok = bool(torch.allclose(flat, want, atol=1e-6, rtol=1e-5))
+        open(out_path, "w").write("ok" if ok else "mismatch")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_exchange_world2_gloo(tmp_path):
+    out = str(tmp_path / "dp.txt")
+    port = 30100 + (os.getpid() % 500)
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
+
+
 def test_shard_ranges_cover_and_balance():
     from transformer_tacotron2_b200.sharding import shard_ranges
     for n in (1, 5, 64, 67):

@@ -66,6 +66,7 @@ int tts_finalize_weights(TtsHandle* h);
 /* ---- options ---------------------------------------------------------------------------------- */
 /* "cluster_group": utterances per 8-CTA cluster of the decode kernel, 1..5 (0 = auto: as few as the number of
  *   co-resident clusters allows);  "decode_timestamps": 1 record per-phase timestamps (tts_debug_phase_timestamps);
+ *   "train_graph": 1 (default) replay tts_train_step from a CUDA graph captured on the second step of a shape, 0 eager;
  *   "print_info": print device / cluster geometry to stderr. */
 int tts_set_option(TtsHandle* h, const char* key, int64_t value);
 

@@ -12,7 +12,7 @@ import bench  # noqa: E402
 from transformer_tacotron2_b200.training import Trainer  # noqa: E402
 
 
-def run(B, S, T, steps=5):
+def run(B, S, T, steps=int(os.environ.get("STEPS", "5"))):
     model = bench.synthetic_state_dict()
     tr = Trainer(model, lr=1e-4)
     g = torch.Generator().manual_seed(B + T)

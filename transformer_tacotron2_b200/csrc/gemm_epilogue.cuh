@@ -27,6 +27,7 @@ struct GemmParams {
     const float* alpha_ptr;          // if set, alpha is read from device memory (trainable scalar)
     const int* lens;                 // zero rows with t >= lens[b]
     int drop_site; uint64_t seed; int utt_offset;   // p = 0.5 bit dropout after the activation (site < 0: off)
+    const uint64_t* seed_ptr;        // if set, the seed is read from device memory (training steps replayed from a CUDA graph)
     int dropw_site; uint32_t dropw_thresh; float dropw_scale;   // word dropout (training, P12) of (acc + bias + alpha * pe), BEFORE the residual
     float* out_f32; bf16* out_bf16; int ldo;
     int scatter;                     // GemmScatter
@@ -41,6 +42,7 @@ TTS_D void gemm_store(const GemmParams& p, int m, int n, float v0, float v1) {
     if (m >= p.M || n >= p.N) return;
     const bool has1 = (n + 1) < p.N;
     const int b = m / p.T, t = m - b * p.T;
+    const uint64_t seed = p.seed_ptr ? *p.seed_ptr : p.seed;
     if (p.bias) { v0 += p.bias[n]; if (has1) v1 += p.bias[n + 1]; }
     if (p.pe) {
         const float alpha = p.alpha_ptr ? *p.alpha_ptr : p.alpha;
@@ -49,7 +51,7 @@ TTS_D void gemm_store(const GemmParams& p, int m, int n, float v0, float v1) {
     }
     if (p.dropw_site >= 0) {                         // n even: words n % 4 and n % 4 + 1 of chunk n / 4
         const uint4 w = philox4x32_10(make_uint4((uint32_t)p.dropw_site, (uint32_t)t, (uint32_t)(p.utt_offset + b), (uint32_t)(n >> 2)),
-                                      (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+                                      (uint32_t)seed, (uint32_t)(seed >> 32));
         const uint32_t w0 = (n & 2) ? w.z : w.x, w1 = (n & 2) ? w.w : w.y;
         v0 = w0 >= p.dropw_thresh ? v0 * p.dropw_scale : 0.f;
         v1 = w1 >= p.dropw_thresh ? v1 * p.dropw_scale : 0.f;
@@ -65,8 +67,8 @@ TTS_D void gemm_store(const GemmParams& p, int m, int n, float v0, float v1) {
     if (p.act == ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
     else if (p.act == ACT_TANH) { v0 = tanhf(v0); v1 = tanhf(v1); }
     if (p.drop_site >= 0) {
-        v0 = keep_bit(p.seed, p.drop_site, t, p.utt_offset + b, n) ? 2.f * v0 : 0.f;
-        if (has1) v1 = keep_bit(p.seed, p.drop_site, t, p.utt_offset + b, n + 1) ? 2.f * v1 : 0.f;
+        v0 = keep_bit(seed, p.drop_site, t, p.utt_offset + b, n) ? 2.f * v0 : 0.f;
+        if (has1) v1 = keep_bit(seed, p.drop_site, t, p.utt_offset + b, n + 1) ? 2.f * v1 : 0.f;
     }
     if (p.lens && t >= p.lens[b]) { v0 = 0.f; v1 = 0.f; }
     if (p.scatter == SC_CROSS_KV || p.scatter == SC_CROSS_KV_VT) {

@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                         gemm_store(g, m, nb0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
                 } else {                                 // thread = one output row: 32 consecutive columns, 16-byte accesses
                     const int bb = m / g.T, tt = m - bb * g.T;
+                    const uint64_t seed = g.seed_ptr ? *g.seed_ptr : g.seed;
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const uint4 w4 = philox4x32_10(make_uint4((uint32_t)g.dropw_site, (uint32_t)tt, (uint32_t)(g.utt_offset + bb), (uint32_t)((nb0 + j) >> 2)),
-                                                           (uint32_t)g.seed, (uint32_t)(g.seed >> 32));
+                                                           (uint32_t)seed, (uint32_t)(seed >> 32));
                             f[j] = w4.x >= g.dropw_thresh ? f[j] * g.dropw_scale : 0.f;
                             f[j + 1] = w4.y >= g.dropw_thresh ? f[j + 1] * g.dropw_scale : 0.f;
                             f[j + 2] = w4.z >= g.dropw_thresh ? f[j + 2] * g.dropw_scale : 0.f;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                     }
                     if (g.drop_site >= 0) {              // 32 aligned columns = one Philox word (P16)
                         const uint4 w4 = philox4x32_10(make_uint4((uint32_t)g.drop_site, (uint32_t)tt, (uint32_t)(g.utt_offset + bb), (uint32_t)(nb0 >> 7)),
-                                                       (uint32_t)g.seed, (uint32_t)(g.seed >> 32));
+                                                       (uint32_t)seed, (uint32_t)(seed >> 32));
                         const uint32_t wi = (nb0 >> 5) & 3u;
                         const uint32_t bits = wi == 0 ? w4.x : wi == 1 ? w4.y : wi == 2 ? w4.z : w4.w;
 #pragma unroll

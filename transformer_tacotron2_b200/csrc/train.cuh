@@ -35,6 +35,18 @@ struct TtsTrain {
     TrEnc enc[6];
     TrDec dec[6];
     int step = 0;
+    PackDesc* pack_descs = nullptr; int n_pack = 0, pack_blocks = 0;
+    // the whole forward + loss + backward of one shape as a CUDA graph (~640 launches, launch-bound otherwise): captured on the
+    // second step with the same key, replayed afterwards
+    struct GraphKey {
+        void* ws; int B, S, T, utt0; double p_res; float pos_weight; float* loss_out; cudaStream_t st;
+        bool operator==(const GraphKey& o) const {
+            return ws == o.ws && B == o.B && S == o.S && T == o.T && utt0 == o.utt0 && p_res == o.p_res && pos_weight == o.pos_weight && loss_out == o.loss_out && st == o.st;
+        }
+    } graph_key{}, seen_key{};
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    unsigned long long graph_launches = 0;
 };
 
 namespace {
@@ -42,7 +54,9 @@ namespace {
 int train_free(TtsHandle* h) {
     if (!h->train) return 0;
     TtsTrain* t = h->train;
-    for (void* p : {(void*)t->P, (void*)t->G, (void*)t->M1, (void*)t->V2, (void*)t->RS, (void*)t->wpack}) if (p) cudaFree(p);
+    if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
+    if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
+    for (void* p : {(void*)t->P, (void*)t->G, (void*)t->M1, (void*)t->V2, (void*)t->RS, (void*)t->wpack, (void*)t->pack_descs}) if (p) cudaFree(p);
     delete t;
     h->train = nullptr;
     return 0;
@@ -67,6 +81,7 @@ struct TrWs {
     float *dx, *dxa, *dq32, *dsum;
     bf16 *dsub, *dwide, *dqkv, *dctx, *dkv, *dhead, *dcv, *dcv2;
     int *plens, *mlens;
+    int64_t* ph_in; float* mels_in; uint64_t* seed_dev;     // staged inputs: a captured step only ever reads workspace memory
     static TrWs make(unsigned char* base, int B, int S, int T) {
         TrWs w; size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return base + r; };
@@ -100,6 +115,7 @@ struct TrWs {
         w.dkv = (bf16*)take(Me * 6144 * 2); w.dhead = (bf16*)take(Md * 128 * 2);
         w.dcv = (bf16*)take(Mx * 512 * 2); w.dcv2 = (bf16*)take(Mx * 512 * 2);
         w.plens = (int*)take((size_t)B * 4); w.mlens = (int*)take((size_t)B * 4);
+        w.ph_in = (int64_t*)take(Me * 8); w.mels_in = (float*)take(Md * 80 * 4); w.seed_dev = (uint64_t*)take(64);
         w.total = o;
         return w;
     }
@@ -200,19 +216,29 @@ int train_build(TtsHandle* h) {
     }
     CK(cudaMemcpy(t->P, host.data(), t->n * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(t->RS, hrs.data(), t->nrs * 4, cudaMemcpyHostToDevice));
-    for (auto& m : t->mats) { m.fwd = t->wpack + m.fwd_off; m.bwd = t->wpack + m.bwd_off; }
+    std::vector<PackDesc> descs;
+    int blk = 0;
+    for (auto& m : t->mats) {
+        m.fwd = t->wpack + m.fwd_off; m.bwd = t->wpack + m.bwd_off;
+        for (int flip = 0; flip < 2; ++flip) {
+            PackDesc d; memset(&d, 0, sizeof(d));
+            d.src_off = (long)m.off; d.dst_off = (long)(flip ? m.bwd_off : m.fwd_off); d.N = m.N; d.K = m.K; d.taps = m.taps;
+            d.R = flip ? m.Kw : m.Nw; d.Cc = flip ? m.Np : m.Kp; d.flip = flip; d.blk0 = blk;
+            blk += (int)(((long)d.taps * d.R * d.Cc + 2047) / 2048);
+            descs.push_back(d);
+        }
+    }
+    t->n_pack = (int)descs.size(); t->pack_blocks = blk;
+    CK(cudaMalloc(&t->pack_descs, descs.size() * sizeof(PackDesc)));
+    CK(cudaMemcpy(t->pack_descs, descs.data(), descs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice));
     return 0;
 }
 
-// bf16 operand copies of every matrix from the fp32 master
+// bf16 operand copies of every matrix from the fp32 master (one launch over the descriptor table)
 int train_repack(TtsHandle* h, cudaStream_t st) {
     TtsTrain* t = h->train;
-    for (auto& m : t->mats) {
-        const long nf = (long)m.taps * m.Nw * m.Kp, nb = (long)m.taps * m.Kw * m.Np;
-        cast_pack_kernel<<<(unsigned)std::min<long>((nf + 255) / 256, 4096), 256, 0, st>>>(t->P + m.off, m.fwd, m.N, m.K, m.taps, m.Nw, m.Kp, 0);
-        cast_pack_kernel<<<(unsigned)std::min<long>((nb + 255) / 256, 4096), 256, 0, st>>>(t->P + m.off, m.bwd, m.N, m.K, m.taps, m.Kw, m.Np, 1);
-        launch_counter() += 2;
-    }
+    cast_pack_all_kernel<<<t->pack_blocks, 256, 0, st>>>(t->pack_descs, t->n_pack, t->P, t->wpack);
+    ++launch_counter();
     CK(cudaGetLastError());
     return 0;
 }
@@ -220,7 +246,7 @@ int train_repack(TtsHandle* h, cudaStream_t st) {
 // ---- one forward + loss + backward -------------------------------------------------------------------------------------
 struct TrCtx {
     TtsHandle* h; TtsTrain* t; TrWs w; cudaStream_t st;
-    int B, S, T; uint64_t seed; int utt0; uint32_t thresh; float dscale;
+    int B, S, T; const uint64_t* seed; int utt0; uint32_t thresh; float dscale;   // seed: device scalar (graph replays read the new value)
     float* P; float* G;
 };
 
@@ -230,7 +256,7 @@ struct TrCtx {
 GemmParams tr_fwd(TrCtx& c, const bf16* A, int lda, int M, int Trows, const TrLin& l) {
     const TrMat& m = c.t->mats[l.mat];
     GemmParams p = gp(A, lda, m.fwd, m.Kp, M, m.N, m.Kp);
-    p.T = Trows; p.B = M / Trows; p.bias = c.P + l.b; p.seed = c.seed; p.utt_offset = c.utt0;
+    p.T = Trows; p.B = M / Trows; p.bias = c.P + l.b; p.seed_ptr = c.seed; p.utt_offset = c.utt0;
     return p;
 }
 void tr_dropw(TrCtx& c, GemmParams& p, int site) {
@@ -298,7 +324,7 @@ int tr_conv_fwd(TrCtx& c, const TrConv& cv, const bf16* in, int ldin, int M, int
     p.taps = 5; p.T = Trows; p.B = M / Trows; p.bias = c.P + cv.b; p.out_f32 = pre; p.ldo = m.N;
     TRL(launch_gemm_tc(p, c.st));
     TRL(cudaMemsetAsync(stat, 0, 1024 * 4, c.st));
-    const dim3 g((m.N + 127) / 128, 64);
+    const dim3 g((m.N + 127) / 128, 592);
     bn_stats_kernel<<<g, 128, 0, c.st>>>(pre, M, m.N, Trows, c.B, lens, stat, 0);
     bn_stats_kernel<<<g, 128, 0, c.st>>>(pre, M, m.N, Trows, c.B, lens, stat, 1);
     bn_act_fwd_kernel<<<std::min<long>(((long)M * m.N + 255) / 256, 2368), 256, 0, c.st>>>(pre, M, m.N, Trows, c.B, lens, stat, c.P + cv.g, c.P + cv.be, c.h->cfg.bn_eps, act,
@@ -312,7 +338,7 @@ template <typename TD>
 int tr_conv_bwd(TrCtx& c, const TrConv& cv, const TD* dout, int ldd, const float* pre, const float* stat, const bf16* in, int ldin, int M, int Trows,
                 const int* lens, int act, int site, bf16* dpre, bf16* din16, int ldi) {
     const TrMat& m = c.t->mats[cv.mat];
-    const dim3 g((m.N + 127) / 128, 64);
+    const dim3 g((m.N + 127) / 128, 592);
     bn_bwd_reduce_kernel<TD><<<g, 128, 0, c.st>>>(dout, ldd, pre, M, m.N, Trows, c.B, lens, stat, c.P + cv.g, c.P + cv.be, c.h->cfg.bn_eps, act, site, c.seed,
                                                   c.utt0, c.G + cv.be, c.G + cv.g);
     bn_bwd_apply_kernel<TD><<<std::min<long>(((long)M * m.N + 255) / 256, 2368), 256, 0, c.st>>>(dout, ldd, pre, M, m.N, Trows, c.B, lens, stat, c.P + cv.g, c.P + cv.be,
@@ -329,11 +355,12 @@ int tr_conv_bwd(TrCtx& c, const TrConv& cv, const TD* dout, int ldd, const float
     return 0;
 }
 
-int train_forward_backward(TrCtx& c, const int64_t* ph, const float* mels, float* loss_out, float pos_weight) {
+int train_forward_backward(TrCtx& c, float* loss_out, float pos_weight) {
     TtsHandle* h = c.h; TtsTrain* t = c.t; TrWs& w = c.w; cudaStream_t st = c.st;
     const int B = c.B, S = c.S, T = c.T, Me = B * S, Md = B * T;
     const float eps = h->cfg.ln_eps;
     const int* plens = w.plens; const int* mlens = w.mlens;
+    const int64_t* ph = w.ph_in; const float* mels = w.mels_in;
     TRL(cudaMemsetAsync(c.G, 0, t->n * 4, st));
 
     // ================================================================ forward (train mode)
@@ -483,7 +510,7 @@ int train_forward_backward(TrCtx& c, const int64_t* ph, const float* mels, float
         TRL(launch_gemm_tc(p, st));
     }
     {   // decoder prenet
-        dropw_bwd_kernel<<<1184, 256, 0, st>>>(w.dx, w.dsub, Md, T, c.thresh ? SITE_DEC_PE : -1, c.seed, c.utt0, c.thresh, c.dscale, h->pe, c.G + t->dec_alpha);
+        dropw_bwd_kernel<<<1184, 256, 0, st>>>(w.dx, w.dsub, Md, T, c.thresh ? (int)SITE_DEC_PE : -1, c.seed, c.utt0, c.thresh, c.dscale, h->pe, c.G + t->dec_alpha);
         ++launch_counter();
         int r;
         if ((r = tr_wgrad(c, w.dsub, 512, w.h2, 256, Md, T, t->dproj.mat, t->dproj.b))) return r;
@@ -527,7 +554,7 @@ int train_forward_backward(TrCtx& c, const int64_t* ph, const float* mels, float
         TRL(launch_gemm_tc(p, st));
     }
     {   // encoder prenet
-        dropw_bwd_kernel<<<592, 256, 0, st>>>(w.dx, w.dsub, Me, S, c.thresh ? SITE_ENC_PE : -1, c.seed, c.utt0, c.thresh, c.dscale, h->pe, c.G + t->enc_alpha);
+        dropw_bwd_kernel<<<592, 256, 0, st>>>(w.dx, w.dsub, Me, S, c.thresh ? (int)SITE_ENC_PE : -1, c.seed, c.utt0, c.thresh, c.dscale, h->pe, c.G + t->enc_alpha);
         ++launch_counter();
         int r;
         if ((r = tr_wgrad(c, w.dsub, 512, w.e[3], 512, Me, S, t->enc_proj.mat, t->enc_proj.b))) return r;
@@ -545,5 +572,7 @@ int train_forward_backward(TrCtx& c, const int64_t* ph, const float* mels, float
     TRL(cudaGetLastError());
     return 0;
 }
+
+__global__ void set_u64_kernel(uint64_t* p, uint64_t v) { *p = v; }
 
 }  // namespace

@@ -12,32 +12,22 @@ namespace tts {
 // ---------------------------------------------------------------------------------------------- weights
 // fp32 master w[(n * K + k) * taps + tap]  ->  bf16 out[tap][n][k]  ([taps][Nw][Kp], zero padded)          (flip = 0)
 //                                          ->  bf16 out[tap][k][n] = w[.. taps-1-tap]  ([taps][Kw][Np])      (flip = 1, dgrad)
-__global__ void cast_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int N, int K, int taps, int R, int Cc, int flip) {
-    const long total = (long)taps * R * Cc;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Cc), r = (int)((i / Cc) % R), tap = (int)(i / ((long)Cc * R));
-        const int n = flip ? c : r, k = flip ? r : c, st = flip ? taps - 1 - tap : tap;
-        out[i] = __float2bfloat16((n < N && k < K) ? w[((long)n * K + k) * taps + st] : 0.f);
-    }
-}
-
-// out[(c * taps + tap)][m] = x[b][t + tap - taps/2][c] (0 outside the utterance), m = b * T + t; out row stride Mp
-__global__ void transpose_shift_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int C, int T, int M, int Mp, int taps) {
-    __shared__ bf16 tile[32][33];
-    const int tap = blockIdx.z, m0 = blockIdx.x * 32, c0 = blockIdx.y * 32, sh = tap - (taps >> 1);
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int m = m0 + i, c = c0 + threadIdx.x;
-        bf16 v = __float2bfloat16(0.f);
-        if (m < M && c < C) {
-            const int t = m % T + sh;
-            if (t >= 0 && t < T) v = x[(long)(m + sh) * ldx + c];
+// every matrix of the model in ONE launch: block -> descriptor (binary search over the first-block table), 2048 elements per block
+struct PackDesc { long src_off, dst_off; int N, K, taps, R, Cc, flip; int blk0; int pad_; };
+__global__ void __launch_bounds__(256) cast_pack_all_kernel(const PackDesc* __restrict__ descs, int nd, const float* __restrict__ P, bf16* __restrict__ wpack) {
+    int lo = 0, hi = nd - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (descs[mid].blk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1; }
+    const PackDesc d = descs[lo];
+    const long total = (long)d.taps * d.R * d.Cc, base = (long)(blockIdx.x - d.blk0) * 2048;
+    const float* w = P + d.src_off; bf16* out = wpack + d.dst_off;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const long i = base + j * 256 + threadIdx.x;
+        if (i < total) {
+            const int c = (int)(i % d.Cc), r = (int)((i / d.Cc) % d.R), tap = (int)(i / ((long)d.Cc * d.R));
+            const int n = d.flip ? c : r, k = d.flip ? r : c, st = d.flip ? d.taps - 1 - tap : tap;
+            out[i] = __float2bfloat16((n < d.N && k < d.K) ? w[((long)n * d.K + k) * d.taps + st] : 0.f);
         }
-        tile[i][threadIdx.x] = v;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i, m = m0 + threadIdx.x;
-        if (c < C && m < Mp) out[(long)(c * taps + tap) * Mp + m] = tile[threadIdx.x][i];
     }
 }
 
@@ -73,9 +63,10 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int M, int C, int T
 
 // y = mask * dropbits( act( (x - mean) * rstd * gamma + beta ) ); optional running-stat update by block 0
 __global__ void bn_act_fwd_kernel(const float* __restrict__ x, int M, int C, int T, int B, const int* __restrict__ lens, const float* __restrict__ stat,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, int site, uint64_t seed,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, int site, const uint64_t* seedp,
                                   int utt_offset, bf16* __restrict__ out16, int ldo, float* __restrict__ out32, float* run_mean, float* run_var,
                                   float momentum) {
+    const uint64_t seed = *seedp;
     const float n = n_valid(lens, B);
     const long total = (long)M * C;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -110,10 +101,11 @@ TTS_D float bn_dact(float dout, float xhat_gb, int act, int site, uint64_t seed,
 template <typename TD>
 __global__ void bn_bwd_reduce_kernel(const TD* __restrict__ dout, int ldd, const float* __restrict__ x, int M, int C, int T, int B,
                                      const int* __restrict__ lens, const float* __restrict__ stat, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, float eps, int act, int site, uint64_t seed, int utt_offset, float* __restrict__ dbeta,
+                                     const float* __restrict__ beta, float eps, int act, int site, const uint64_t* seedp, int utt_offset, float* __restrict__ dbeta,
                                      float* __restrict__ dgamma) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
+    const uint64_t seed = *seedp;
     const float n = n_valid(lens, B);
     const float mean = stat[c] / n, rstd = rsqrtf(stat[C + c] / n + eps), ga = gamma[c], be = beta[c];
     const int rows = (M + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
@@ -131,8 +123,9 @@ __global__ void bn_bwd_reduce_kernel(const TD* __restrict__ dout, int ldd, const
 template <typename TD>
 __global__ void bn_bwd_apply_kernel(const TD* __restrict__ dout, int ldd, const float* __restrict__ x, int M, int C, int T, int B,
                                     const int* __restrict__ lens, const float* __restrict__ stat, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, float eps, int act, int site, uint64_t seed, int utt_offset,
+                                    const float* __restrict__ beta, float eps, int act, int site, const uint64_t* seedp, int utt_offset,
                                     const float* __restrict__ dbeta, const float* __restrict__ dgamma, bf16* __restrict__ dx, int ldx) {
+    const uint64_t seed = *seedp;
     const float n = n_valid(lens, B);
     const long total = (long)M * C;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -153,9 +146,10 @@ __global__ void bn_bwd_apply_kernel(const TD* __restrict__ dout, int ldd, const 
 // Outputs: dy32 (the residual path) and dsub16 = dy * keep / (1 - p) of the sub-layer's residual-dropout site (site < 0: plain copy).
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ ypre, const float* __restrict__ gamma,
                                                      float eps, int M, int T, float* __restrict__ dy32, bf16* __restrict__ dsub16, int site,
-                                                     uint64_t seed, int utt_offset, uint32_t thresh, float dscale, float* __restrict__ dgamma,
+                                                     const uint64_t* seedp, int utt_offset, uint32_t thresh, float dscale, float* __restrict__ dgamma,
                                                      float* __restrict__ dbeta) {
     __shared__ float sg[512], sb[512];
+    const uint64_t seed = *seedp;
     for (int i = threadIdx.x; i < 512; i += 256) { sg[i] = 0.f; sb[i] = 0.f; }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -233,8 +227,9 @@ __global__ void relu_bwd_kernel(bf16* __restrict__ d, const bf16* __restrict__ s
 }
 
 // word-dropout backward of a [M][512] fp32 gradient -> bf16, plus dalpha += sum d * keep * scale * pe[t][c]
-__global__ void dropw_bwd_kernel(const float* __restrict__ d, bf16* __restrict__ out, int M, int T, int site, uint64_t seed, int utt_offset,
+__global__ void dropw_bwd_kernel(const float* __restrict__ d, bf16* __restrict__ out, int M, int T, int site, const uint64_t* seedp, int utt_offset,
                                  uint32_t thresh, float dscale, const float* __restrict__ pe, float* __restrict__ dalpha) {
+    const uint64_t seed = *seedp;
     float acc = 0.f;
     const long total4 = (long)M * 128;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {

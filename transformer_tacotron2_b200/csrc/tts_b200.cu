@@ -57,6 +57,7 @@ struct TtsHandle {
     bool dec_active = false; int dec_B = 0, dec_S = 0, dec_T = 0, dec_t = 0; uint64_t dec_seed = 0; int dec_utt0 = 0;
     int* h_status = nullptr;                                          // pinned: t_done, n_finished
     TtsTrain* train = nullptr;                                        // training state (train.cuh), built by tts_train_begin
+    int train_graph = 1;                                              // replay the train step from a CUDA graph (option "train_graph")
 };
 
 #define CK(call)                                                                                     \
@@ -146,6 +147,7 @@ extern "C" int tts_set_option(TtsHandle* h, const char* key, int64_t value) {
     if (!h || !key) return TTS_E_ARG;
     if (!strcmp(key, "decode_timestamps")) { h->decode_timestamps = value ? 1 : 0; return 0; }
     if (!strcmp(key, "cluster_group")) { if (value < 0 || value > CL_G) FAIL(TTS_E_ARG, "cluster_group must be 0 (auto) or 1..5"); h->cluster_group = (int)value; return 0; }
+    if (!strcmp(key, "train_graph")) { h->train_graph = value ? 1 : 0; return 0; }
     if (!strcmp(key, "print_info")) { fprintf(stderr, "[tts_b200] sms=%d cluster_ok=%d max_clusters=%d group=%d ngroups=%d\n", h->num_sms, h->cluster_ok, h->max_clusters, h->cparams.G, h->cparams.ngroups); return 0; }
     FAIL(TTS_E_ARG, std::string("unknown option ") + key);
 }
@@ -877,13 +879,50 @@ extern "C" int tts_train_step(TtsHandle* h, void* ws, const int64_t* phonemes, c
     if (p_residual < 0.0 || p_residual >= 1.0) FAIL(TTS_E_ARG, "p_residual out of range");
     CK(cudaSetDevice(h->device));
     TrCtx c;
-    c.h = h; c.t = h->train; c.w = TrWs::make(reinterpret_cast<unsigned char*>(ws), B, S, T); c.st = (cudaStream_t)stream;
-    c.B = B; c.S = S; c.T = T; c.seed = seed; c.utt0 = utt_offset;
+    TtsTrain* t = h->train;
+    c.h = h; c.t = t; c.w = TrWs::make(reinterpret_cast<unsigned char*>(ws), B, S, T); c.st = (cudaStream_t)stream;
+    c.B = B; c.S = S; c.T = T; c.seed = c.w.seed_dev; c.utt0 = utt_offset;
     c.thresh = (uint32_t)(p_residual * 4294967296.0); c.dscale = 1.0f / (float)(1.0 - p_residual);
-    c.P = h->train->P; c.G = h->train->G;
+    c.P = t->P; c.G = t->G;
+    // stage the inputs: the step itself (eager or replayed from its CUDA graph) reads workspace memory only
     CK(cudaMemcpyAsync(c.w.plens, phoneme_lens, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
     CK(cudaMemcpyAsync(c.w.mlens, mel_lens, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
-    return train_forward_backward(c, phonemes, mels, loss_out, pos_weight);
+    CK(cudaMemcpyAsync(c.w.ph_in, phonemes, (size_t)B * S * 8, cudaMemcpyDeviceToDevice, c.st));
+    CK(cudaMemcpyAsync(c.w.mels_in, mels, (size_t)B * T * 80 * 4, cudaMemcpyDeviceToDevice, c.st));
+    set_u64_kernel<<<1, 1, 0, c.st>>>(c.w.seed_dev, seed);
+    ++launch_counter();
+    const TtsTrain::GraphKey key{ws, B, S, T, utt_offset, p_residual, pos_weight, loss_out, c.st};
+    if (h->train_graph && t->graph_exec && key == t->graph_key) {
+        CK(cudaGraphLaunch(t->graph_exec, c.st));
+        launch_counter() += t->graph_launches;
+        return 0;
+    }
+    if (h->train_graph && key == t->seen_key) {                          // second step of this shape: capture, then replay
+        if (t->graph_exec) { cudaGraphExecDestroy(t->graph_exec); t->graph_exec = nullptr; }
+        const unsigned long long l0 = launch_counter();
+        cudaGraph_t graph = nullptr;
+        // (the caller's stream may be the legacy default stream, which cannot be captured: record on a stream of our own)
+        if (!t->cap_stream) CK(cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking));
+        cudaStream_t user_st = c.st;
+        c.st = t->cap_stream;
+        CK(cudaStreamBeginCapture(c.st, cudaStreamCaptureModeThreadLocal));
+        int r = train_forward_backward(c, loss_out, pos_weight);
+        cudaError_t e = cudaStreamEndCapture(c.st, &graph);
+        c.st = user_st;
+        if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+        CK(e);
+        t->graph_launches = launch_counter() - l0;
+        launch_counter() = l0;
+        e = cudaGraphInstantiate(&t->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CK(e);
+        t->graph_key = key;
+        CK(cudaGraphLaunch(t->graph_exec, c.st));
+        launch_counter() += t->graph_launches;
+        return 0;
+    }
+    t->seen_key = key;
+    return train_forward_backward(c, loss_out, pos_weight);
 }
 extern "C" int tts_train_outputs(TtsHandle* h, void* ws, int B, int S, int T, float* mel_before, float* mel_after, float* stop_logits, void* stream) {
     if (!h || !ws || !h->train) return TTS_E_ARG;

@@ -161,12 +161,20 @@ __global__ void __launch_bounds__(256) colsum8_kernel(const bf16* __restrict__ x
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    if (cg < C8 && rlane < rl)
-        for (int m = blockIdx.x * rl + rlane; m < M; m += gridDim.x * rl) {
-            const uint4 v = *reinterpret_cast<const uint4*>(x + (size_t)m * ld + cg * 8);
-            const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
-            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    if (cg < C8 && rlane < rl) {
+        const int stride = gridDim.x * rl;
+        for (int m = blockIdx.x * rl + rlane; m < M; m += 4 * stride) {                 // 4 independent 16-byte loads in flight
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                v[u] = (m + u * stride < M) ? *reinterpret_cast<const uint4*>(x + (size_t)(m + u * stride) * ld + cg * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 a = unpack_bf16x2(v[u].x), b = unpack_bf16x2(v[u].y), c = unpack_bf16x2(v[u].z), d = unpack_bf16x2(v[u].w);
+                acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+            }
         }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
     __syncthreads();
@@ -217,7 +225,7 @@ inline cudaError_t launch_wgrad_tc(const WgradParams& g, cudaStream_t stream) {
         const int M = g.T * g.nb;
         if ((g.Cout & 7) == 0) {
             const int C8 = g.Cout / 8, cpb = std::min(C8, 256);
-            colsum8_kernel<<<dim3(num_sms, (C8 + cpb - 1) / cpb), 256, 0, stream>>>(g.dY, g.ldy, M, C8, cpb, g.dbias);
+            colsum8_kernel<<<dim3(4 * num_sms, (C8 + cpb - 1) / cpb), 256, 0, stream>>>(g.dY, g.ldy, M, C8, cpb, g.dbias);
         } else {
             colsum_kernel<bf16><<<dim3((g.Cout + 127) / 128, 256), 128, 0, stream>>>(g.dY, g.ldy, M, g.Cout, g.dbias);
         }

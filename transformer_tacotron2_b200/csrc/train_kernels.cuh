@@ -31,17 +31,6 @@ __global__ void __launch_bounds__(256) cast_pack_all_kernel(const PackDesc* __re
     }
 }
 
-// out[c] += sum_m x[m][c]
-template <typename TI>
-__global__ void colsum_kernel(const TI* __restrict__ x, int ld, int M, int C, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const int rows = (M + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
-    float acc = 0.f;
-    for (int m = r0; m < r1; ++m) acc += to_f32(x[(long)m * ld + c]);
-    if (r1 > r0) atomicAdd(out + c, acc);
-}
-
 // ---------------------------------------------------------------------------------------------- masked BatchNorm (P5)
 TTS_D float n_valid(const int* lens, int B) { int n = 0; for (int b = 0; b < B; ++b) n += lens[b]; return (float)max(n, 1); }
 

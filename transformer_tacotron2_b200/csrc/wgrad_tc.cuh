@@ -7,6 +7,8 @@
 // The output is tiny (<= 6144 x 512) while the reduction is long (25.6k-51.2k tokens), so every output tile is split along
 // the token axis (split-K) to fill the 148 SMs; partial tiles are added with red.global.add.f32 into the zeroed gradient
 // buffer.  Persistent CTAs, 192 threads (TMA warp / MMA warp / 4 epilogue warps), double-buffered TMEM accumulator.
+// The bias gradient (column sums of dY) rides along: the items of the first n-tile / tap issue one extra N = 16 MMA per
+// k-step against a tile of ones, so db = dY^T . 1 comes out of the tensor pipe into 16 spare TMEM columns.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -20,7 +22,7 @@ struct WgradParams {
     const bf16* X; int ldx; int Cin;
     int taps, T, nb;                  // rows per utterance, utterances (M = nb * T)
     float* dW;                        // [Cout][Cin * taps] fp32, accumulated
-    float* dbias;                     // optional [Cout]: += column sums of dY (added by the n-tile 0 / tap 0 items)
+    float* dbias;                     // optional [Cout]: += column sums of dY (by the n-tile 0 / tap 0 items, via a ones-tile MMA)
 };
 
 struct WgradTcParams {
@@ -31,12 +33,14 @@ struct WgradTcParams {
 };
 
 constexpr int WG_STAGES = 4, WG_STAGE_BYTES = 32768, WG_THREADS = 192;
-constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 256;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 2048 + 256;    // ring + ones tile + barriers
+constexpr uint32_t WG_IDESC_ONES = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr uint32_t WG_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
     extern __shared__ __align__(1024) unsigned char wg_smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(wg_smem + WG_STAGES * WG_STAGE_BYTES);
+    unsigned char* ones = wg_smem + WG_STAGES * WG_STAGE_BYTES;         // [16 tokens][64 features] of bf16 1.0
+    uint64_t* full = reinterpret_cast<uint64_t*>(ones + 2048);
     uint64_t* empty = full + WG_STAGES;
     uint64_t* tmem_full = empty + WG_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -45,6 +49,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const WgradParams& g = p.g;
     const int pad = g.taps >> 1;
 
+    for (int i = threadIdx.x; i < 512; i += WG_THREADS) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
         if (tc_smem_u32(wg_smem) & 1023) __trap();
         for (int s = 0; s < WG_STAGES; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512) : "memory");   // 2 x 128 dW + 2 x 16 db columns
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -85,9 +91,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         if (lane == 0) {                                 // ---------------- MMA issuer
             uint32_t it = 0, j = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++j) {
-                const int sp = item % p.splits;
+                const int tile = item / p.splits, sp = item - tile * p.splits;
+                const bool do_bias = g.dbias && (tile % (g.taps * p.tiles_n)) == 0;      // first n-tile, tap 0
                 const int kb0 = sp * p.kb_per_split, kb1 = min(p.n_kb, kb0 + p.kb_per_split);
                 const uint32_t acc = j & 1, ause = j >> 1;
+                const uint32_t ones_addr = tc_smem_u32(ones);
                 if (ause > 0) tc_mbar_wait(&tmem_empty[acc], (ause & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + acc * 128;
@@ -99,6 +107,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 #pragma unroll
                     for (int k = 0; k < 4; ++k)          // 16 tokens per MMA = 16 rows x 128 B inside each box
                         ft_mma(d_tmem, fb_desc_mn(a_addr + k * 2048, 8192), fb_desc_mn(b_addr + k * 2048, 8192), WG_IDESC, (kb > kb0) || k != 0);
+                    if (do_bias) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ft_mma(tmem_base + 256 + acc * 16, fb_desc_mn(a_addr + k * 2048, 8192), fb_desc_mn(ones_addr, 16), WG_IDESC_ONES, (kb > kb0) || k != 0);
+                    }
                     ft_commit(&empty[s]);
                 }
                 ft_commit(&tmem_full[acc]);
@@ -119,6 +132,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             }
             const int n = mt * 128 + lg * 32 + lane;
             const int ldo = g.Cin * g.taps;
+            if (nonempty && g.dbias && nt == 0 && tap == 0) {                            // db[n] += sum_tokens dY[token][n]
+                uint32_t bv[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(bv[0]), "=r"(bv[1]), "=r"(bv[2]), "=r"(bv[3]), "=r"(bv[4]), "=r"(bv[5]), "=r"(bv[6]), "=r"(bv[7]),
+                               "=r"(bv[8]), "=r"(bv[9]), "=r"(bv[10]), "=r"(bv[11]), "=r"(bv[12]), "=r"(bv[13]), "=r"(bv[14]), "=r"(bv[15])
+                             : "r"(tmem_base + 256 + acc * 16 + ((uint32_t)(lg * 32) << 16)));
+                ft_ld_wait();
+                if (n < g.Cout) atomicAdd(g.dbias + n, __uint_as_float(bv[0]));
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < 128; c0 += 32) {
                 uint32_t v[32];
@@ -148,43 +170,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
-    }
-}
-
-// dbias[c] += sum_m x[m][c] : 8 columns per thread (16-byte loads); a block covers cpb column groups x (256 / cpb) row lanes,
-// rows strided over the grid; row lanes are summed in shared memory before the atomics
-__global__ void __launch_bounds__(256) colsum8_kernel(const bf16* __restrict__ x, int ld, int M, int C8, int cpb, float* __restrict__ out) {
-    __shared__ float red[256 * 8];
-    const int rl = 256 / cpb, cl = threadIdx.x % cpb, rlane = threadIdx.x / cpb;
-    const int cg = blockIdx.y * cpb + cl;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    if (cg < C8 && rlane < rl) {
-        const int stride = gridDim.x * rl;
-        for (int m = blockIdx.x * rl + rlane; m < M; m += 4 * stride) {                 // 4 independent 16-byte loads in flight
-            uint4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                v[u] = (m + u * stride < M) ? *reinterpret_cast<const uint4*>(x + (size_t)(m + u * stride) * ld + cg * 8) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float2 a = unpack_bf16x2(v[u].x), b = unpack_bf16x2(v[u].y), c = unpack_bf16x2(v[u].z), d = unpack_bf16x2(v[u].w);
-                acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
-    __syncthreads();
-    if (rlane == 0 && cg < C8) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float t = 0.f;
-            for (int r = 0; r < rl; ++r) t += red[(r * cpb + cl) * 8 + i];
-            atomicAdd(out + cg * 8 + i, t);
-        }
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -221,16 +207,6 @@ inline cudaError_t launch_wgrad_tc(const WgradParams& g, cudaStream_t stream) {
     const int grid = std::min(p.n_items, num_sms);
     wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(p);
     ++launch_counter();
-    if (g.dbias) {
-        const int M = g.T * g.nb;
-        if ((g.Cout & 7) == 0) {
-            const int C8 = g.Cout / 8, cpb = std::min(C8, 256);
-            colsum8_kernel<<<dim3(4 * num_sms, (C8 + cpb - 1) / cpb), 256, 0, stream>>>(g.dY, g.ldy, M, C8, cpb, g.dbias);
-        } else {
-            colsum_kernel<bf16><<<dim3((g.Cout + 127) / 128, 256), 128, 0, stream>>>(g.dY, g.ldy, M, g.Cout, g.dbias);
-        }
-        ++launch_counter();
-    }
     return cudaGetLastError();
 }
 

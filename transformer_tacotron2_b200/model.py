@@ -217,7 +217,8 @@ class TransformerTTS(nn.Module):
         """phonemes [B,S] i64, phoneme_lens [B], mels [B,T,80] f32, mel_lens [B]
         -> mel_before [B,T,80], mel_after [B,T,80], stop_logits [B,T]  (on the GPU, zero past mel_lens)."""
         if self.training:
-            raise NotImplementedError("training-mode forward/backward is not built yet (SURVEY.md 8(f)); use .eval()")
+            raise NotImplementedError("train-mode steps go through transformer_tacotron2_b200.training.Trainer (forward + loss + backward in the library); "
+                                      "this method is the eval-mode forward")
         lib = self._ensure_handle()
         self.sync_weights()
         dev = self.device

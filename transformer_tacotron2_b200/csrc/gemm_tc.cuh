@@ -3,12 +3,12 @@
 // i.e. plain GEMMs (taps = 1, T = M) and conv1d(k = 5, pad = 2) as 5 row-shifted GEMMs accumulated into ONE
 // TMEM accumulator; rows outside [0, T) of their own utterance are zero-filled by TMA's out-of-bounds handling
 // (the A operand is a 3-D tensor map {channels, frames, utterances}), so no padded copies exist.
-// Structure (persistent: one CTA per SM walks 128 x 128 output tiles; 192 threads; the TMEM accumulator is double-buffered
+// Structure (persistent: one CTA per SM walks 128 x 128 output tiles; 320 threads; the TMEM accumulator is double-buffered
 // so the epilogue of tile i overlaps the mainloop of tile i+1):
 //   warp 0  : TMA producer      cp.async.bulk.tensor -> 4-stage shared-memory ring (128B swizzle), mbarrier full/empty
 //   warp 1  : MMA issuer        one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N128 K16), accumulator
 //                               in TMEM (128 fp32 columns); tcgen05.commit releases ring slots / signals the epilogue
-//   warps 2-5: epilogue         tcgen05.ld 32x32b (thread = output row) -> fused epilogue of gemm_epilogue.cuh (bias, BN fold,
+//   warps 2-9: epilogue         tcgen05.ld 32x32b (thread = output row) -> fused epilogue of gemm_epilogue.cuh (bias, BN fold,
 //                               ReLU / tanh, residual, alpha*PE, length mask, Philox dropout, KV scatter, head split)
 #pragma once
 #include <cuda.h>
@@ -21,7 +21,8 @@ namespace tts {
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 4;
 constexpr int TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2;              // 32 KB
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256;   // + alignment slack + barriers
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                                           // two warps per TMEM lane quarter, 64 columns each
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 struct GemmTcParams {
     alignas(64) CUtensorMap tm_a;     // bf16 {K (inner), T, B}, box {64, 128, 1}, SWIZZLE_128B
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { tc_mbar_init(&tmem_full[a], 1); tc_mbar_init(&tmem_empty[a], TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tm_w) : "memory");
@@ -131,8 +132,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&tmem_full[acc])) : "memory");
             }
         }
-    } else {                                             // ---------------- epilogue warps 2..5
+    } else {                                             // ---------------- epilogue warps 2..9
         const int lg = warp & 3;                         // TMEM lane group this warp may access: lanes 32*lg .. 32*lg+31
+        const int chalf = (warp - 2) >> 2;               // which 64 columns of the tile (the epilogue is latency-bound: 8 warps halve it)
         uint32_t j = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
         const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * TC_BN;
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const int t = t0 + lg * 32 + lane;
         const int m = b * p.Tl + t;
 #pragma unroll 1
-        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        for (int c0 = chalf * 64; c0 < chalf * 64 + 64; c0 += 32) {
             uint32_t v[32];
             const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"

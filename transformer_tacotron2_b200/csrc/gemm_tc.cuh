@@ -18,15 +18,17 @@
 
 namespace tts {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 4;
-constexpr int TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2;              // 32 KB
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256;   // + alignment slack + barriers
-constexpr int TC_EPI_WARPS = 8;                                           // two warps per TMEM lane quarter, 64 columns each
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4;
+constexpr int TC_EPI_WARPS = 8;                                           // two warps per TMEM lane quarter, half of the columns each
+constexpr int TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2;              // 48 KB
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_EPI_WARPS * 4096 + 1024 + 256;   // ring + output staging + alignment slack + barriers
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 struct GemmTcParams {
     alignas(64) CUtensorMap tm_a;     // bf16 {K (inner), T, B}, box {64, 128, 1}, SWIZZLE_128B
     alignas(64) CUtensorMap tm_w;     // bf16 {K (inner), taps * Nw}, box {64, 128}, SWIZZLE_128B
+    alignas(64) CUtensorMap tm_out;   // output {N (inner), T, B}: fp32 box {32, 32, 1} / bf16 box {64, 32, 1}, SWIZZLE_128B (TMA store)
+    int tma_out;                      // 0 = direct stores, 1 = fp32 via TMA store, 2 = bf16 via TMA store
     GemmParams g;                     // shapes + epilogue (A / W pointers unused here)
     int Tl;                           // rows per A-tensor slab: T for convs (taps > 1), M for plain GEMMs
     int tiles_per_utt;                // ceil(Tl / 128)
@@ -64,7 +66,8 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    unsigned char* ostage = smem + TC_STAGES * TC_STAGE_BYTES;          // [TC_EPI_WARPS][4 KB] output staging for the TMA stores
+    uint64_t* full = reinterpret_cast<uint64_t*>(ostage + TC_EPI_WARPS * 4096);
     uint64_t* empty = full + TC_STAGES;
     uint64_t* tmem_full = empty + TC_STAGES;             // [2]
     uint64_t* tmem_empty = tmem_full + 2;                // [2]
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
     } else {                                             // ---------------- epilogue warps 2..9
         const int lg = warp & 3;                         // TMEM lane group this warp may access: lanes 32*lg .. 32*lg+31
-        const int chalf = (warp - 2) >> 2;               // which 64 columns of the tile (the epilogue is latency-bound: 8 warps halve it)
+        const int chalf = (warp - 2) >> 2;               // which half of the tile's columns (the epilogue is latency-bound: 8 warps halve it)
         uint32_t j = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++j) {
         const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * TC_BN;
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const int t = t0 + lg * 32 + lane;
         const int m = b * p.Tl + t;
 #pragma unroll 1
-        for (int c0 = chalf * 64; c0 < chalf * 64 + 64; c0 += 32) {
+        for (int c0 = chalf * (TC_BN / 2); c0 < (chalf + 1) * (TC_BN / 2); c0 += 32) {
             uint32_t v[32];
             const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -156,90 +159,129 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                          : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (t < p.Tl && m < g.M) {
+            {
                 const int nb0 = n0 + c0;
-                const bool vec = g.scatter == SC_NONE && nb0 + 32 <= g.N && (g.ldo & 7) == 0 && (g.ldr & 7) == 0;
+                const bool rvalid = t < p.Tl && m < g.M;
+                const bool vec = g.scatter == SC_NONE && nb0 + 32 <= g.N && (g.ldo & 7) == 0 && (g.ldr & 7) == 0;      // warp-uniform
                 if (!vec) {
+                    if (rvalid) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2)
-                        gemm_store(g, m, nb0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                } else {                                 // thread = one output row: 32 consecutive columns, 16-byte accesses
-                    const int bb = m / g.T, tt = m - bb * g.T;
-                    const uint64_t seed = g.seed_ptr ? *g.seed_ptr : g.seed;
+                        for (int j = 0; j < 32; j += 2)
+                            gemm_store(g, m, nb0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                    }
+                } else {                                 // thread = one output row: 32 consecutive columns
                     float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (g.bias) {
+                    for (int j = 0; j < 32; ++j) f[j] = 0.f;
+                    if (rvalid) {
+                        const int bb = m / g.T, tt = m - bb * g.T;
+                        const uint64_t seed = g.seed_ptr ? *g.seed_ptr : g.seed;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb0 + j));
-                            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        if (g.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb0 + j));
+                                f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+                            }
                         }
-                    }
-                    if (g.pe) {
-                        const float alpha = g.alpha_ptr ? *g.alpha_ptr : g.alpha;
+                        if (g.pe) {
+                            const float alpha = g.alpha_ptr ? *g.alpha_ptr : g.alpha;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 pv = __ldg(reinterpret_cast<const float4*>(g.pe + (size_t)tt * kDModel + nb0 + j));
-                            f[j] += alpha * pv.x; f[j + 1] += alpha * pv.y; f[j + 2] += alpha * pv.z; f[j + 3] += alpha * pv.w;
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 pv = __ldg(reinterpret_cast<const float4*>(g.pe + (size_t)tt * kDModel + nb0 + j));
+                                f[j] += alpha * pv.x; f[j + 1] += alpha * pv.y; f[j + 2] += alpha * pv.z; f[j + 3] += alpha * pv.w;
+                            }
                         }
-                    }
-                    if (g.dropw_site >= 0) {             // word dropout (P12): 4 consecutive columns = one Philox call
+                        if (g.dropw_site >= 0) {             // word dropout (P12): 4 consecutive columns = one Philox call
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const uint4 w4 = philox4x32_10(make_uint4((uint32_t)g.dropw_site, (uint32_t)tt, (uint32_t)(g.utt_offset + bb), (uint32_t)((nb0 + j) >> 2)),
+                            for (int j = 0; j < 32; j += 4) {
+                                const uint4 w4 = philox4x32_10(make_uint4((uint32_t)g.dropw_site, (uint32_t)tt, (uint32_t)(g.utt_offset + bb), (uint32_t)((nb0 + j) >> 2)),
+                                                               (uint32_t)seed, (uint32_t)(seed >> 32));
+                                f[j] = w4.x >= g.dropw_thresh ? f[j] * g.dropw_scale : 0.f;
+                                f[j + 1] = w4.y >= g.dropw_thresh ? f[j + 1] * g.dropw_scale : 0.f;
+                                f[j + 2] = w4.z >= g.dropw_thresh ? f[j + 2] * g.dropw_scale : 0.f;
+                                f[j + 3] = w4.w >= g.dropw_thresh ? f[j + 3] * g.dropw_scale : 0.f;
+                            }
+                        }
+                        if (g.resid_bf16) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                const uint4 rv = *reinterpret_cast<const uint4*>(g.resid_bf16 + (size_t)m * g.ldr + nb0 + j);
+                                const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y), r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
+                                f[j] += r0.x; f[j + 1] += r0.y; f[j + 2] += r1.x; f[j + 3] += r1.y;
+                                f[j + 4] += r2.x; f[j + 5] += r2.y; f[j + 6] += r3.x; f[j + 7] += r3.y;
+                            }
+                        }
+                        if (g.resid_f32) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 rv = *reinterpret_cast<const float4*>(g.resid_f32 + (size_t)m * g.ldr + nb0 + j);
+                                f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
+                            }
+                        }
+                        if (g.act == ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                        } else if (g.act == ACT_TANH) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+                        }
+                        if (g.drop_site >= 0) {              // 32 aligned columns = one Philox word (P16)
+                            const uint4 w4 = philox4x32_10(make_uint4((uint32_t)g.drop_site, (uint32_t)tt, (uint32_t)(g.utt_offset + bb), (uint32_t)(nb0 >> 7)),
                                                            (uint32_t)seed, (uint32_t)(seed >> 32));
-                            f[j] = w4.x >= g.dropw_thresh ? f[j] * g.dropw_scale : 0.f;
-                            f[j + 1] = w4.y >= g.dropw_thresh ? f[j + 1] * g.dropw_scale : 0.f;
-                            f[j + 2] = w4.z >= g.dropw_thresh ? f[j + 2] * g.dropw_scale : 0.f;
-                            f[j + 3] = w4.w >= g.dropw_thresh ? f[j + 3] * g.dropw_scale : 0.f;
+                            const uint32_t wi = (nb0 >> 5) & 3u;
+                            const uint32_t bits = wi == 0 ? w4.x : wi == 1 ? w4.y : wi == 2 ? w4.z : w4.w;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = ((bits >> j) & 1u) ? 2.f * f[j] : 0.f;
+                        }
+                        if (g.lens && tt >= g.lens[bb]) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = 0.f;
                         }
                     }
-                    if (g.resid_bf16) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const uint4 rv = *reinterpret_cast<const uint4*>(g.resid_bf16 + (size_t)m * g.ldr + nb0 + j);
-                            const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y), r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
-                            f[j] += r0.x; f[j + 1] += r0.y; f[j + 2] += r1.x; f[j + 3] += r1.y;
-                            f[j + 4] += r2.x; f[j + 5] += r2.y; f[j + 6] += r3.x; f[j + 7] += r3.y;
+                    // Output: a thread-per-row store instruction touches 32 different lines (32 L1->XBAR requests); instead the
+                    // warp writes its 32 x 128-byte chunk into 128B-swizzled staging and one lane issues a TMA tensor store
+                    // (rows past T / M are clipped by the tensor map).  bf16: two 32-column chunks share one 128-byte-wide box.
+                    const int half = (c0 >> 5) & 1;
+                    const bool use_tma = p.tma_out == 1 || (p.tma_out == 2 && n0 + (c0 & ~63) + 64 <= g.N);
+                    if (use_tma) {
+                        unsigned char* st = ostage + (warp - 2) * 4096 + lane * 128;
+                        if (p.tma_out == 1 || half == 0) {
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // previous store has read the staging
+                            __syncwarp();
                         }
-                    }
-                    if (g.resid_f32) {
+                        if (p.tma_out == 1) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 rv = *reinterpret_cast<const float4*>(g.resid_f32 + (size_t)m * g.ldr + nb0 + j);
-                            f[j] += rv.x; f[j + 1] += rv.y; f[j + 2] += rv.z; f[j + 3] += rv.w;
+                            for (int q = 0; q < 8; ++q)
+                                *reinterpret_cast<float4*>(st + ((q ^ (lane & 7)) << 4)) = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                *reinterpret_cast<uint4*>(st + (((half * 4 + q) ^ (lane & 7)) << 4)) =
+                                    make_uint4(pack_bf16x2(f[q * 8], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]), pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
                         }
-                    }
-                    if (g.act == ACT_RELU) {
+                        if (p.tma_out == 1 || half == 1) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {
+                                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                             ::"l"(&p.tm_out), "r"(p.tma_out == 1 ? nb0 : nb0 - 32), "r"(t0 + lg * 32), "r"(b), "r"(tc_smem_u32(ostage + (warp - 2) * 4096)) : "memory");
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
+                        }
+                    } else if (rvalid) {
+                        if (g.out_f32) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                    } else if (g.act == ACT_TANH) {
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(g.out_f32 + (size_t)m * g.ldo + nb0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        }
+                        if (g.out_bf16) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
-                    }
-                    if (g.drop_site >= 0) {              // 32 aligned columns = one Philox word (P16)
-                        const uint4 w4 = philox4x32_10(make_uint4((uint32_t)g.drop_site, (uint32_t)tt, (uint32_t)(g.utt_offset + bb), (uint32_t)(nb0 >> 7)),
-                                                       (uint32_t)seed, (uint32_t)(seed >> 32));
-                        const uint32_t wi = (nb0 >> 5) & 3u;
-                        const uint32_t bits = wi == 0 ? w4.x : wi == 1 ? w4.y : wi == 2 ? w4.z : w4.w;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = ((bits >> j) & 1u) ? 2.f * f[j] : 0.f;
-                    }
-                    if (g.lens && tt >= g.lens[bb]) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = 0.f;
-                    }
-                    if (g.out_f32) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(g.out_f32 + (size_t)m * g.ldo + nb0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    }
-                    if (g.out_bf16) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            *reinterpret_cast<uint4*>(g.out_bf16 + (size_t)m * g.ldo + nb0 + j) =
-                                make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]), pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
+                            for (int j = 0; j < 32; j += 8)
+                                *reinterpret_cast<uint4*>(g.out_bf16 + (size_t)m * g.ldo + nb0 + j) =
+                                    make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]), pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
+                        }
                     }
                 }
             }
@@ -249,6 +291,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&tmem_empty[acc])) : "memory");   // accumulator free
         }
     }
+    if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this warp's TMA stores are complete
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -302,6 +345,20 @@ inline cudaError_t launch_gemm_tc(const GemmParams& g, cudaStream_t stream) {
         if (enc(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(g.W), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
+    }
+    p.tma_out = 0;
+    if (g.scatter == SC_NONE && (g.out_f32 != nullptr) != (g.out_bf16 != nullptr)) {
+        const bool f32 = g.out_f32 != nullptr;
+        const size_t es = f32 ? 4 : 2;
+        void* base = f32 ? (void*)g.out_f32 : (void*)g.out_bf16;
+        if (((size_t)g.ldo * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (g.ldo & 7) == 0 && (g.ldr & 7) == 0) {
+            const cuuint64_t dims[3] = {(cuuint64_t)g.N, (cuuint64_t)p.Tl, (cuuint64_t)nb};
+            const cuuint64_t strides[2] = {(cuuint64_t)g.ldo * es, (cuuint64_t)g.ldo * es * p.Tl};
+            const cuuint32_t box[3] = {f32 ? 32u : 64u, 32, 1};
+            if (enc(&p.tm_out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                p.tma_out = f32 ? 1 : 2;
+        }
     }
     p.n_tiles_n = (g.N + TC_BN - 1) / TC_BN;
     p.n_tiles = p.n_tiles_n * nb * p.tiles_per_utt;

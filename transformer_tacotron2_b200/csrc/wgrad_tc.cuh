@@ -199,8 +199,19 @@ inline cudaError_t launch_wgrad_tc(const WgradParams& g, cudaStream_t stream) {
     p.tiles_m = (g.Cout + 127) / 128; p.tiles_n = (g.Cin + 127) / 128;
     p.n_tiles = p.tiles_m * p.tiles_n * g.taps;
     p.kb_per_utt = (g.T + 63) / 64; p.n_kb = p.kb_per_utt * g.nb;
-    int splits = (2 * num_sms + p.n_tiles - 1) / p.n_tiles;              // ~2 work items per SM
-    splits = std::max(1, std::min(splits, (p.n_kb + 3) / 4));            // at least 4 token blocks per item
+    // split-K factor: enough items to fill the SMs (>= ~2 per SM), at least 4 token blocks per item, and a total that
+    // lands just under a whole number of waves (a 2.2-wave launch wastes a quarter of the machine)
+    const int max_splits = std::max(1, (p.n_kb + 3) / 4);
+    int splits = 1; double best = -1.0;
+    for (int sp = 1; sp <= max_splits && sp <= 64; ++sp) {
+        const int kbs = (p.n_kb + sp - 1) / sp, real = (p.n_kb + kbs - 1) / kbs;
+        const long items = (long)p.n_tiles * real;
+        const long waves = (items + num_sms - 1) / num_sms;
+        double eff = (double)items / (double)(waves * num_sms);
+        if (items < 2L * num_sms) eff *= (double)items / (2.0 * num_sms);   // too few items: pipeline prologue / epilogue exposed
+        eff -= 0.004 * real;                                                // every split adds one round of atomics
+        if (eff > best) { best = eff; splits = real; }
+    }
     p.kb_per_split = (p.n_kb + splits - 1) / splits;
     p.splits = (p.n_kb + p.kb_per_split - 1) / p.kb_per_split;
     p.n_items = p.n_tiles * p.splits;

@@ -62,5 +62,17 @@ for (B, L, causal) in [(32, 400, 1), (32, 800, 1), (16, 1600, 1), (64, 100, 0), 
     tf = fl / ms / 1e9
     out.append(dict(kernel="flash attention fwd", B=B, L=L, causal=causal, ms=ms, tflops=tf, frac_of_measured_peak=tf / PEAK))
     print(f"attention B={B} L={L} causal={causal}: {ms:7.3f} ms  {tf:7.1f} TFLOP/s  ({tf / PEAK:.1%})")
+for (B, L, causal) in [(32, 800, 1), (64, 800, 1), (8, 4096, 0)]:
+    H = 8
+    Q = torch.randn(B, L, H * 64, device="cuda").to(torch.bfloat16); K_ = torch.randn_like(Q); V = torch.randn_like(Q); O = torch.empty_like(Q)
+    dO = torch.randn_like(Q); dQ, dK, dV = torch.empty_like(Q), torch.empty_like(Q), torch.empty_like(Q)
+    kl = torch.full((B,), L, dtype=torch.int32, device="cuda"); lse = torch.empty(B, H, L, device="cuda")
+    scratch = torch.empty(B * L * H * 64 + B * H * L, device="cuda")
+    lib.tts_k_attention_lse(P(Q), P(K_), P(V), P(O), P(lse), P(kl), B, H, L, L, causal, ST())
+    ms = timeit(lambda: lib.tts_k_attention_bwd(P(Q), P(K_), P(V), P(O), P(dO), P(lse), P(kl), P(dQ), P(dK), P(dV), P(scratch), B, H, L, L, causal, ST()))
+    fl = 10.0 * B * H * 64 * (L * (L + 1) / 2 if causal else L * L)
+    tf = fl / ms / 1e9
+    out.append(dict(kernel="flash attention bwd (incl. dsum / dQ cast passes)", B=B, L=L, causal=causal, ms=ms, tflops=tf, frac_of_measured_peak=tf / PEAK))
+    print(f"attention bwd B={B} L={L} causal={causal}: {ms:7.3f} ms  {tf:7.1f} TFLOP/s  ({tf / PEAK:.1%})")
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/seq_kernels.json", "w"), indent=1)

@@ -155,3 +155,28 @@ def test_graph_replay_equals_eager(oracle_model):
     assert eager[0] != eager[3]                                        # the seed matters
     for a, b in zip(eager, graph):
         assert abs(a - b) <= 1e-3 * abs(a), (eager, graph)
+
+
+def test_trained_weights_flow_back_into_inference(oracle_model):
+    """Trainer.export_to_module(): after a few optimiser steps the module's state_dict carries the trained parameters and
+    BatchNorm statistics; loading that state_dict into the oracle and running the eval-mode forward on both sides agrees
+    (the training state and the inference weights are the same numbers)."""
+    from oracle import synthetic
+    from transformer_tacotron2_b200.training import Trainer
+    inputs = synthetic.make_inputs(3, 16, 40, 8, True)
+    model = make_b200_model(oracle_model)
+    tr = Trainer(model, lr=2e-4)
+    for i in range(3):
+        tr.step(*inputs, seed=50 + i)
+    tr.export_to_module()
+    sd = model.state_dict()
+    assert any(not torch.equal(sd[k], v) for k, v in oracle_model.state_dict().items() if v.is_floating_point())
+    trained = copy.deepcopy(oracle_model).eval()
+    # the kernels read bf16 copies of the matrices; give the oracle the same effective weights so that the comparison
+    # measures the flow-back (values, BatchNorm folding of the NEW statistics), not weight quantisation
+    trained.load_state_dict({k: (v.to(torch.bfloat16).to(torch.float32) if v.is_floating_point() and v.dim() >= 2 else v) for k, v in sd.items()})
+    with torch.no_grad():
+        want = trained(*inputs, seed=7)
+    got = model(*inputs, seed=7)
+    for name, g, w in zip(("mel_before", "mel_after", "stop_logits"), got, want):
+        assert rel_l2(g, w) < 2e-2, (name, rel_l2(g, w))

@@ -8,7 +8,7 @@
 //                             dV += P^T dO, dK += dS^T Q   M128(keys) N64 K128(q): A = the bf16 P / dS tile in shared memory
 //                                                          read as an MN-major operand, B = dO_i / Q_i as MN-major
 //                             dQ_i = dS K_j               M128(q) N64 K128(keys): A = dS K-major, B = K_j MN-major
-//   warps 2..5  thread = query row: S -> P (bf16, swizzled store), dP -> dS, then dQ_i from TMEM -> fp32 red.add into the
+//   warps 2..9  thread = query row x half of the columns: S -> P (bf16, swizzled store), dP -> dS, then dQ_i from TMEM -> fp32 red.add into the
 //               dQ accumulator (several key tiles add into the same rows); at the end dK_j, dV_j -> bf16.
 #pragma once
 #include <cuda.h>
@@ -34,7 +34,8 @@ struct AttnBwdTcParams {
     AttnBwdParams a;
 };
 
-constexpr int FB_THREADS = 192;
+constexpr int FB_CWARPS = 8;                                        // compute warps: two per TMEM lane quarter, half of the columns each
+constexpr int FB_THREADS = 64 + 32 * FB_CWARPS;
 constexpr int FB_TILE = 128 * 64 * 2;                               // 16 KB
 constexpr int FB_SMEM_BYTES = 10 * FB_TILE + 256;                   // K, V, Q[2], dO[2], P (2 halves), dS (2 halves)
 constexpr int FB_COL_S = 0, FB_COL_DP = 128, FB_COL_DV = 256, FB_COL_DK = 320, FB_COL_DQ = 384;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
         if (tc_smem_u32(fb_smem) & 1023) __trap();
         tc_mbar_init(kv_full, 1);
         for (int s = 0; s < 2; ++s) { tc_mbar_init(&qd_full[s], 1); tc_mbar_init(&qd_empty[s], 1); }
-        tc_mbar_init(s_full, 1); tc_mbar_init(sdp_empty, 4); tc_mbar_init(ds_full, 4); tc_mbar_init(mma3_done, 1);
+        tc_mbar_init(s_full, 1); tc_mbar_init(sdp_empty, FB_CWARPS); tc_mbar_init(ds_full, FB_CWARPS); tc_mbar_init(mma3_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
             }
         }
     } else if (ni > 0) {                                 // ---------------- thread = query row of the tile
-        const int lg = warp & 3, r = lg * 32 + lane;
+        const int lg = warp & 3, r = lg * 32 + lane, ch = (warp - 2) >> 2;     // ch: which half of the columns this warp owns
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
         for (int it = 0; it < ni; ++it) {
             const int qi = (i0 + it) * 128 + r;
@@ -150,9 +151,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
             tc_mbar_wait(s_full, it & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (it > 0) tc_mbar_wait(mma3_done, (it - 1) & 1);               // the MMAs that read the previous P / dS are complete
-            uint32_t pr[64];                                                 // P as bf16 pairs, kept for dS
+            uint32_t pr[32];                                                 // P (this warp's 64 keys) as bf16 pairs, kept for dS
 #pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 32) {
                 uint32_t v[32];
                 ft_ld32_nowait(lane_addr + FB_COL_S + c0, v);
                 ft_ld_wait();
@@ -160,24 +161,24 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
                 for (int i = 0; i < 32; i += 2) {
                     const float p0 = (c0 + i < kmax) ? fast_exp2(__uint_as_float(v[i]) * a.scale_log2 - L) : 0.f;
                     const float p1 = (c0 + i + 1 < kmax) ? fast_exp2(__uint_as_float(v[i + 1]) * a.scale_log2 - L) : 0.f;
-                    pr[(c0 + i) >> 1] = pack_bf16x2(p0, p1);
+                    pr[((c0 & 63) + i) >> 1] = pack_bf16x2(p0, p1);
                 }
                 unsigned char* half = sP + (c0 >> 6) * FB_TILE + r * 128;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int chunk = ((c0 & 63) >> 3) + q, w = (c0 >> 1) + q * 4;
+                    const int chunk = ((c0 & 63) >> 3) + q, w = ((c0 & 63) >> 1) + q * 4;
                     *reinterpret_cast<uint4*>(half + ((chunk ^ (r & 7)) << 4)) = make_uint4(pr[w], pr[w + 1], pr[w + 2], pr[w + 3]);
                 }
             }
 #pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 32) {
                 uint32_t v[32];
                 ft_ld32_nowait(lane_addr + FB_COL_DP + c0, v);
                 ft_ld_wait();
                 uint32_t ds[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    const float2 pp = unpack_bf16x2(pr[(c0 + i) >> 1]);
+                    const float2 pp = unpack_bf16x2(pr[((c0 & 63) + i) >> 1]);
                     ds[i >> 1] = pack_bf16x2(pp.x * (__uint_as_float(v[i]) - Dr) * a.scale, pp.y * (__uint_as_float(v[i + 1]) - Dr) * a.scale);
                 }
                 unsigned char* half = sdS + (c0 >> 6) * FB_TILE + r * 128;
@@ -194,8 +195,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
             // dQ_i of this key tile
             tc_mbar_wait(mma3_done, it & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
+            {
+                const int c0 = ch * 32;
                 uint32_t v[32];
                 ft_ld32_nowait(lane_addr + FB_COL_DQ + c0, v);
                 ft_ld_wait();
@@ -212,14 +213,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
         const int ki = k0 + r;
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
-            uint32_t o[64];
-            const uint32_t col = which ? FB_COL_DK : FB_COL_DV;
-            ft_ld32_nowait(lane_addr + col, o); ft_ld32_nowait(lane_addr + col + 32, o + 32);
+            uint32_t o[32];
+            const uint32_t col = (which ? FB_COL_DK : FB_COL_DV) + ch * 32;
+            ft_ld32_nowait(lane_addr + col, o);
             ft_ld_wait();
             if (ki < a.Lk) {
-                bf16* g = which ? a.dK + b * a.dk_bs + h * a.dk_hs + (long)ki * a.dk_rs : a.dV + b * a.dv_bs + h * a.dv_hs + (long)ki * a.dv_rs;
+                bf16* g = (which ? a.dK + b * a.dk_bs + h * a.dk_hs + (long)ki * a.dk_rs : a.dV + b * a.dv_bs + h * a.dv_hs + (long)ki * a.dv_rs) + ch * 32;
 #pragma unroll
-                for (int i = 0; i < 64; i += 8)
+                for (int i = 0; i < 32; i += 8)
                     *reinterpret_cast<uint4*>(g + i) = make_uint4(pack_bf16x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])),
                                                                   pack_bf16x2(__uint_as_float(o[i + 2]), __uint_as_float(o[i + 3])),
                                                                   pack_bf16x2(__uint_as_float(o[i + 4]), __uint_as_float(o[i + 5])),
@@ -228,12 +229,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {                                             // key tile that no query sees (all keys padded): zero gradients
-        const int r = (warp & 3) * 32 + lane, ki = k0 + r;
+        const int r = (warp & 3) * 32 + lane, ki = k0 + r, ch = (warp - 2) >> 2;
         if (ki < a.Lk) {
-            bf16* gk = a.dK + b * a.dk_bs + h * a.dk_hs + (long)ki * a.dk_rs;
-            bf16* gv = a.dV + b * a.dv_bs + h * a.dv_hs + (long)ki * a.dv_rs;
+            bf16* gk = a.dK + b * a.dk_bs + h * a.dk_hs + (long)ki * a.dk_rs + ch * 32;
+            bf16* gv = a.dV + b * a.dv_bs + h * a.dv_hs + (long)ki * a.dv_rs + ch * 32;
 #pragma unroll
-            for (int i = 0; i < 64; i += 8) { *reinterpret_cast<uint4*>(gk + i) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(gv + i) = make_uint4(0, 0, 0, 0); }
+            for (int i = 0; i < 32; i += 8) { *reinterpret_cast<uint4*>(gk + i) = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(gv + i) = make_uint4(0, 0, 0, 0); }
         }
     }
     __syncthreads();

@@ -279,9 +279,22 @@ def run_b200(args, rank, world, local_rank):
         t1e.record()
         barrier()
         train_ms = max_over_ranks(t0e.elapsed_time(t1e)) / args.steps
+        # tensor roofline of the step: algorithmic FLOPs = 3 x forward (28.14 / 52.88 GF per utterance at
+        # S = 100, T = 400 / 800; backward = 2 x forward) against the measured sustained bf16 rate
+        fwd_gf = {400: 28.14, 800: 52.88}.get(Tt) if S == 100 else None
+        tpeak = None
+        try:
+            tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        except Exception:
+            tpeak = None
+        troof = None
+        if fwd_gf and tpeak:
+            ach = 3.0 * fwd_gf * Bt / (train_ms * 1e-3) / 1e3
+            troof = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                     "algorithmic_gflop_per_step_per_gpu": 3.0 * fwd_gf * Bt}
         train = {"metric": "utterances/s, teacher-forced train step (forward + loss + backward + all-reduce + Adam)",
                  "value": world * Bt / (train_ms * 1e-3), "unit": "utt/s", "ms_per_step": train_ms, "loss": float(loss),
-                 "gpu_launches_per_step": int((lib.tts_launch_count() - launches_t0) // args.steps),
+                 "gpu_launches_per_step": int((lib.tts_launch_count() - launches_t0) // args.steps), "roofline": troof,
                  "config": {"workload": f"configs[3]: base model train step, B={Bt}/GPU, S={S}, T={Tt}, bf16 operands / fp32 accumulate, "
                                         f"fp32 master + Adam, data parallel x{world} (one NCCL all-reduce over 53.0 M fp32 gradients)"}}
         tr = None

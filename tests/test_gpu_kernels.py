@@ -29,7 +29,8 @@ def _stream():
 
 
 @pytest.mark.parametrize("M,N,K,act", [(128, 128, 32, 0), (300, 512, 512, 1), (1, 128, 96, 0), (777, 1536, 512, 0),
-                                         (130, 512, 2048, 2), (6400, 256, 256, 1)])
+                                         (130, 512, 2048, 2), (6400, 256, 256, 1), (257, 384, 72, 0), (4097, 640, 520, 1),
+                                         (33, 896, 8, 0)])
 def test_gemm(lib, M, N, K, act):
     g = torch.Generator().manual_seed(M + N + K)
     A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
@@ -44,7 +45,8 @@ def test_gemm(lib, M, N, K, act):
     assert torch.allclose(Cout, ref, atol=2e-3, rtol=2e-3), float((Cout - ref).abs().max())
 
 
-@pytest.mark.parametrize("B,T,Cin,Cout", [(2, 37, 96, 512), (3, 130, 512, 512), (1, 5, 512, 128), (4, 64, 512, 128)])
+@pytest.mark.parametrize("B,T,Cin,Cout", [(2, 37, 96, 512), (3, 130, 512, 512), (1, 5, 512, 128), (4, 64, 512, 128), (2, 129, 80, 128),
+                                          (5, 300, 512, 256), (3, 1, 512, 384)])
 def test_conv5(lib, B, T, Cin, Cout):
     g = torch.Generator().manual_seed(B * T)
     X = (torch.randn(B, T, Cin, generator=g) * 0.5).to(torch.bfloat16)

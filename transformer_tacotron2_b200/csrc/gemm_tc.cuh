@@ -143,6 +143,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const int mt = tile / p.n_tiles_n, n0 = (tile - mt * p.n_tiles_n) * TC_BN;
         const int b = mt / p.tiles_per_utt, t0 = (mt - b * p.tiles_per_utt) * TC_BM;
         const uint32_t acc = j & 1;
+        // bias of this warp's 128 columns: 4 per lane, fetched once per tile while the MMAs run (a per-chunk __ldg put an L2
+        // round trip into every chunk's dependency chain); the chunks pick their values up by shuffle
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias) {
+            const int bc = n0 + chalf * (TC_BN / 2) + lane * 4;
+            if (bc + 3 < g.N) bq = __ldg(reinterpret_cast<const float4*>(g.bias + bc));
+            else { if (bc < g.N) bq.x = g.bias[bc]; if (bc + 1 < g.N) bq.y = g.bias[bc + 1]; if (bc + 2 < g.N) bq.z = g.bias[bc + 2]; }
+        }
         tc_mbar_wait(&tmem_full[acc], (j >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int t = t0 + lg * 32 + lane;
@@ -171,20 +179,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                     }
                 } else {                                 // thread = one output row: 32 consecutive columns
                     float f[32];
+                    {
+                        const int src0 = (c0 - chalf * (TC_BN / 2)) >> 2;      // lane holding the bias of this chunk's first 4 columns
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = 0.f;
+                        for (int j = 0; j < 32; j += 4) {
+                            f[j] = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bq.x, src0 + (j >> 2));
+                            f[j + 1] = __uint_as_float(v[j + 1]) + __shfl_sync(0xffffffffu, bq.y, src0 + (j >> 2));
+                            f[j + 2] = __uint_as_float(v[j + 2]) + __shfl_sync(0xffffffffu, bq.z, src0 + (j >> 2));
+                            f[j + 3] = __uint_as_float(v[j + 3]) + __shfl_sync(0xffffffffu, bq.w, src0 + (j >> 2));
+                        }
+                    }
                     if (rvalid) {
                         const int bb = m / g.T, tt = m - bb * g.T;
                         const uint64_t seed = g.seed_ptr ? *g.seed_ptr : g.seed;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                        if (g.bias) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb0 + j));
-                                f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
-                            }
-                        }
                         if (g.pe) {
                             const float alpha = g.alpha_ptr ? *g.alpha_ptr : g.alpha;
 #pragma unroll

@@ -18,7 +18,7 @@ timed); `e2e` = the same through TransformerTTS.inference with HOST tensors (H2D
 region); `roofline` = the persistent decode kernel's algorithmic HBM bytes / its CUDA-event duration
 against the measured copy bandwidth; `cpu_baseline` = the oracle on the box's host cores (bounded sample);
 `train` = the other half of BASELINE.json's metric: utterances/s of the full train step (configs[3], B = 32 per GPU,
-data parallel with one all-reduce over the flat gradient buffer), same timing rules.
+data parallel; the gradient exchange is fused into the optimiser kernel over NVLink peer memory), same timing rules.
 """
 from __future__ import annotations
 
@@ -264,7 +264,7 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_train:
         from transformer_tacotron2_b200.training import Trainer
         Bt, Tt = args.train_batch, T
-        tr = Trainer(model, lr=1e-4, world_size=world)
+        tr = Trainer(model, lr=1e-4, world_size=world, rank=rank)
         g = torch.Generator().manual_seed(DATA_SEED + 1000 + rank)
         tph = torch.randint(1, 128, (Bt, S), generator=g).to(dev); tpl = torch.full((Bt,), S, dtype=torch.int32, device=dev)
         tmel = torch.randn(Bt, Tt, 80, generator=g).clamp(-4, 4).to(dev); tml = torch.full((Bt,), Tt, dtype=torch.int32, device=dev)
@@ -296,7 +296,10 @@ def run_b200(args, rank, world, local_rank):
                  "value": world * Bt / (train_ms * 1e-3), "unit": "utt/s", "ms_per_step": train_ms, "loss": float(loss),
                  "gpu_launches_per_step": int((lib.tts_launch_count() - launches_t0) // args.steps), "roofline": troof,
                  "config": {"workload": f"configs[3]: base model train step, B={Bt}/GPU, S={S}, T={Tt}, bf16 operands / fp32 accumulate, "
-                                        f"fp32 master + Adam, data parallel x{world} (one NCCL all-reduce over 53.0 M fp32 gradients)"}}
+                                        f"fp32 master + Adam, data parallel x{world} "
+                                        + ("(gradient exchange fused into the optimiser kernel: reduce-scatter by NVLink peer loads -> Adam on the "
+                                           "rank's shard -> all-gather by peer stores)" if tr._peers else "(single rank: no exchange)" if world == 1
+                                           else "(one NCCL all-reduce over 53.0 M fp32 gradients)")}}
         tr = None
 
     if rank != 0:

@@ -130,6 +130,16 @@ int tts_train_grads(TtsHandle* h, float** grads_dev, int64_t* numel);
 /* Adam over the flat buffers (g <- grad * grad_scale, e.g. 1 / world_size after a sum all-reduce), then refresh the
  * bf16 operand copies. */
 int tts_train_adam(TtsHandle* h, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* Data-parallel optimiser step fused with its collective: CUDA-IPC handles (64 bytes each) of this rank's
+ * flat parameter and gradient buffers; tts_train_set_peers maps every rank's buffers (handles_* = [world][64] bytes, in rank
+ * order; world <= 8, one node).  tts_train_adam_peers then runs ONE kernel that, for this rank's 1/world shard, sums the
+ * gradient over all ranks by NVLink peer loads (reduce-scatter), applies Adam with shard-local moments (ZeRO-1), and stores
+ * the new parameters into every rank's buffer by peer stores (all-gather).  The caller brackets it with two cross-rank
+ * barriers on the stream and calls tts_train_repack afterwards. */
+int tts_train_ipc_handles(TtsHandle* h, void* handle_P_64, void* handle_G_64);
+int tts_train_set_peers(TtsHandle* h, int rank, int world, const void* handles_P, const void* handles_G);
+int tts_train_adam_peers(TtsHandle* h, float lr, float beta1, float beta2, float eps, void* stream);
+int tts_train_repack(TtsHandle* h, void* stream);
 /* Enumerate the tensors inside the flat buffers: state_dict name, offset, numel; is_buffer = 1 for running stats. */
 int tts_train_num_tensors(TtsHandle* h);
 int tts_train_tensor_info(TtsHandle* h, int index, const char** name, int64_t* offset, int64_t* numel, int* is_buffer);

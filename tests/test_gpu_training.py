@@ -180,3 +180,29 @@ def test_trained_weights_flow_back_into_inference(oracle_model):
     got = model(*inputs, seed=7)
     for name, g, w in zip(("mel_before", "mel_after", "stop_logits"), got, want):
         assert rel_l2(g, w) < 2e-2, (name, rel_l2(g, w))
+
+
+def test_peer_adam_kernel_world1_equals_plain_adam(oracle_model):
+    """The fused reduce-scatter -> Adam -> all-gather kernel with a single rank (peers = self) is plain Adam; the multi-GPU
+    behaviour is checked by scripts/dp_peer_check.py under torchrun (needs >= 2 GPUs)."""
+    import ctypes as C
+    from oracle import synthetic
+    from transformer_tacotron2_b200.training import Trainer
+    inputs = synthetic.make_inputs(2, 12, 20, 3, True)
+    res = []
+    for fused in (False, True):
+        model = make_b200_model(oracle_model)
+        tr = Trainer(model, lr=1e-3)
+        tr.forward_backward(*inputs, seed=4)
+        if fused:
+            assert tr._lib.tts_train_set_peers(tr._h, 0, 1, None, None) == 0
+            model._check(tr._lib.tts_train_adam_peers(tr._h, 1e-3, 0.9, 0.98, 1e-9, model._stream()), "adam_peers")
+            model._check(tr._lib.tts_train_repack(tr._h, model._stream()), "repack")
+        else:
+            tr.adam_step()
+        res.append(torch.cat([v.flatten() for _, v in sorted(tr.parameters().items())]))
+    # two separate backward passes: their gradients differ in the last bits (atomic accumulation order), and the first Adam
+    # step is sign-like (lr * g / (|g| + eps)), so elements whose gradient is ~eps may legitimately differ by up to 2 * lr
+    diff = (res[0] - res[1]).abs()
+    assert float((diff > 1e-6).float().mean()) < 1e-3, float((diff > 1e-6).float().mean())
+    assert float(diff.max()) <= 2.1e-3

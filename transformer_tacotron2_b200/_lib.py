@@ -46,6 +46,10 @@ SIGNATURES = {
     "tts_train_outputs": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "tts_train_grads": (_I, [_P, C.POINTER(_P), C.POINTER(_I64)]),
     "tts_train_adam": (_I, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
+    "tts_train_ipc_handles": (_I, [_P, _P, _P]),
+    "tts_train_set_peers": (_I, [_P, _I, _I, _P, _P]),
+    "tts_train_adam_peers": (_I, [_P, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
+    "tts_train_repack": (_I, [_P, _P]),
     "tts_train_num_tensors": (_I, [_P]),
     "tts_train_tensor_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I)]),
     "tts_train_read": (_I, [_P, _I, _I64, _I64, _P]),

@@ -36,6 +36,10 @@ struct TtsTrain {
     TrDec dec[6];
     int step = 0;
     PackDesc* pack_descs = nullptr; int n_pack = 0, pack_blocks = 0;
+    // data-parallel peers (tts_train_set_peers): every rank's P and G buffers mapped through CUDA IPC; P[rank] / G[rank] are local
+    int rank = 0, world = 1;
+    PeerPtrs peers{};
+    void* ipc_opened[16] = {};
     // the whole forward + loss + backward of one shape as a CUDA graph (~640 launches, launch-bound otherwise): captured on the
     // second step with the same key, replayed afterwards
     struct GraphKey {
@@ -54,6 +58,7 @@ namespace {
 int train_free(TtsHandle* h) {
     if (!h->train) return 0;
     TtsTrain* t = h->train;
+    for (void* q : t->ipc_opened) if (q) cudaIpcCloseMemHandle(q);
     if (t->graph_exec) cudaGraphExecDestroy(t->graph_exec);
     if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
     for (void* p : {(void*)t->P, (void*)t->G, (void*)t->M1, (void*)t->V2, (void*)t->RS, (void*)t->wpack, (void*)t->pack_descs}) if (p) cudaFree(p);

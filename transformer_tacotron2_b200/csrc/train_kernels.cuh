@@ -311,4 +311,33 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Data-parallel optimiser step as ONE kernel over NVLink peer memory (ZeRO-1 style): this rank owns the
+// shard [lo, hi) of the flat parameter buffer.  For every element of its shard it reads the gradient from EVERY rank's
+// gradient buffer (reduce-scatter by peer loads), applies Adam with its shard-local moments, and stores the new parameter
+// into EVERY rank's parameter buffer (all-gather by peer stores).  16-byte accesses; no staging buffers, no NCCL ring.
+struct PeerPtrs { float* P[8]; const float* G[8]; };
+__global__ void __launch_bounds__(256) adam_peer_kernel(PeerPtrs pp, int world, float* __restrict__ m, float* __restrict__ v, long lo4, long hi4,
+                                                        float lr, float beta1, float beta2, float eps, float bc1, float bc2, float grad_scale) {
+    const float4* P0 = reinterpret_cast<const float4*>(pp.P[0]);
+    for (long i = lo4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (long)gridDim.x * blockDim.x) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int r = 0; r < world; ++r) {
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(pp.G[r]) + i);
+            g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+        }
+        float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i], p = P0[i];
+        float* gp = &g.x; float* mp = &mm.x; float* vp = &vv.x; float* ppv = &p.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gi = gp[k] * grad_scale;
+            mp[k] = beta1 * mp[k] + (1.f - beta1) * gi;
+            vp[k] = beta2 * vp[k] + (1.f - beta2) * gi * gi;
+            ppv[k] -= lr * (mp[k] / bc1) / (sqrtf(vp[k] / bc2) + eps);
+        }
+        reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+        for (int r = 0; r < world; ++r) __stcg(reinterpret_cast<float4*>(pp.P[r]) + i, p);
+    }
+}
+
 }  // namespace tts

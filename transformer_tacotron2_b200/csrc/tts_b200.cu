@@ -950,6 +950,58 @@ extern "C" int tts_train_adam(TtsHandle* h, float lr, float beta1, float beta2, 
     CK(cudaGetLastError());
     return train_repack(h, st);
 }
+// ---- data-parallel peers: fused reduce-scatter -> Adam -> all-gather over NVLink peer memory -------------------------------
+extern "C" int tts_train_ipc_handles(TtsHandle* h, void* handle_P_64, void* handle_G_64) {
+    if (!h || !h->train || !handle_P_64 || !handle_G_64) return TTS_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(h->device));
+    CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_P_64), h->train->P));
+    CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_G_64), h->train->G));
+    return 0;
+}
+extern "C" int tts_train_set_peers(TtsHandle* h, int rank, int world, const void* handles_P, const void* handles_G) {
+    if (!h || !h->train || world < 1 || world > 8 || rank < 0 || rank >= world || (world > 1 && (!handles_P || !handles_G))) return TTS_E_ARG;
+    CK(cudaSetDevice(h->device));
+    TtsTrain* t = h->train;
+    for (void*& q : t->ipc_opened) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    t->rank = rank; t->world = world;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { t->peers.P[r] = t->P; t->peers.G[r] = t->G; continue; }
+        cudaIpcMemHandle_t hp, hg;
+        memcpy(&hp, reinterpret_cast<const char*>(handles_P) + 64 * r, 64); memcpy(&hg, reinterpret_cast<const char*>(handles_G) + 64 * r, 64);
+        void *pp = nullptr, *pg = nullptr;
+        CK(cudaIpcOpenMemHandle(&pp, hp, cudaIpcMemLazyEnablePeerAccess));
+        t->ipc_opened[2 * r] = pp;
+        CK(cudaIpcOpenMemHandle(&pg, hg, cudaIpcMemLazyEnablePeerAccess));
+        t->ipc_opened[2 * r + 1] = pg;
+        t->peers.P[r] = reinterpret_cast<float*>(pp); t->peers.G[r] = reinterpret_cast<const float*>(pg);
+    }
+    return 0;
+}
+// The caller orders this between two cross-rank barriers on the stream: every rank's backward is complete before, every
+// rank's shard has been written everywhere after (then tts_train_repack refreshes the bf16 operand copies).
+extern "C" int tts_train_adam_peers(TtsHandle* h, float lr, float beta1, float beta2, float eps, void* stream) {
+    if (!h || !h->train) return TTS_E_ARG;
+    CK(cudaSetDevice(h->device));
+    TtsTrain* t = h->train;
+    ++t->step;
+    const float bc1 = 1.f - std::pow(beta1, (float)t->step), bc2 = 1.f - std::pow(beta2, (float)t->step);
+    const long n4 = (long)(t->n / 4), per = (n4 + t->world - 1) / t->world;
+    const long lo4 = std::min(n4, per * t->rank), hi4 = std::min(n4, lo4 + per);
+    PeerPtrs pp = t->peers;
+    if (t->world == 1) { pp.P[0] = t->P; pp.G[0] = t->G; }
+    // local buffer first: the kernel reads the old parameter from P[0]
+    std::swap(pp.P[0], pp.P[t->rank]);
+    adam_peer_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(pp, t->world, t->M1, t->V2, lo4, hi4, lr, beta1, beta2, eps, bc1, bc2, 1.f / (float)t->world);
+    ++launch_counter();
+    CK(cudaGetLastError());
+    return 0;
+}
+extern "C" int tts_train_repack(TtsHandle* h, void* stream) {
+    if (!h || !h->train) return TTS_E_ARG;
+    CK(cudaSetDevice(h->device));
+    return train_repack(h, (cudaStream_t)stream);
+}
 extern "C" int tts_train_num_tensors(TtsHandle* h) { return (h && h->train) ? (int)(h->train->params.size() + h->train->buffers.size()) : -1; }
 extern "C" int tts_train_tensor_info(TtsHandle* h, int index, const char** name, int64_t* offset, int64_t* numel, int* is_buffer) {
     if (!h || !h->train || !name || !offset || !numel || !is_buffer || index < 0) return TTS_E_ARG;

@@ -35,7 +35,8 @@ class _DevBuf:
 
 class Trainer:
     def __init__(self, model: TransformerTTS, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.98), eps: float = 1e-9,
-                 p_residual: float = 0.1, pos_weight: float = 5.0, process_group=None, world_size: int = 1):
+                 p_residual: float = 0.1, pos_weight: float = 5.0, process_group=None, world_size: int = 1, rank: int = 0,
+                 fused_peer_adam: bool = True):
         self.model = model
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.p_residual, self.pos_weight = float(p_residual), float(pos_weight)
@@ -54,6 +55,32 @@ class Trainer:
         for i in range(lib.tts_train_num_tensors(self._h)):
             model._check(lib.tts_train_tensor_info(self._h, i, C.byref(name), C.byref(off), C.byref(numel), C.byref(isb)), "tts_train_tensor_info")
             self._table.append((name.value.decode(), off.value, numel.value, bool(isb.value)))
+        # Data parallel on one node: map every rank's parameter / gradient buffers through CUDA IPC so that the optimiser step
+        # is ONE kernel doing reduce-scatter (peer loads) -> Adam on this rank's shard -> all-gather (peer stores) over NVLink.
+        self.rank, self._peers = int(rank), False
+        if self.world_size > 1 and fused_peer_adam:
+            self._peers = self._map_peers()
+        self._tick = torch.zeros(1, device=model.device)
+
+    def _map_peers(self) -> bool:
+        import torch.distributed as dist
+        hp, hg = C.create_string_buffer(64), C.create_string_buffer(64)
+        self.model._check(self._lib.tts_train_ipc_handles(self._h, hp, hg), "tts_train_ipc_handles")
+        gathered = [None] * self.world_size
+        dist.all_gather_object(gathered, (self.rank, hp.raw, hg.raw), group=self.group)
+        gathered.sort(key=lambda x: x[0])
+        if [x[0] for x in gathered] != list(range(self.world_size)):
+            raise ValueError(f"Trainer(rank=...) must be this process's rank in the group: got ranks {[x[0] for x in gathered]}")
+        allp, allg = b"".join(x[1] for x in gathered), b"".join(x[2] for x in gathered)
+        rc = self._lib.tts_train_set_peers(self._h, self.rank, self.world_size, allp, allg)
+        ok = torch.tensor([1 if rc == 0 else 0], device=self.model.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)              # all ranks take the same path
+        return bool(int(ok.item()))
+
+    def _stream_barrier(self):
+        """Cross-rank barrier ordered on the CUDA stream (no host synchronisation): a 1-element all-reduce."""
+        import torch.distributed as dist
+        dist.all_reduce(self._tick, op=dist.ReduceOp.SUM, group=self.group)
 
     # ------------------------------------------------------------------ one step
     def _workspace(self, B, S, T):
@@ -88,10 +115,22 @@ class Trainer:
         self.model._check(rc, "tts_train_adam")
         self.model._dirty = True          # the module's host copies are stale until export_to_module()
 
+    def adam_step_peers(self):
+        """reduce-scatter + Adam + all-gather in one kernel over NVLink peer memory, bracketed by stream-ordered barriers."""
+        m = self.model
+        self._stream_barrier()                     # every rank's gradients are complete
+        m._check(self._lib.tts_train_adam_peers(self._h, self.lr, self.betas[0], self.betas[1], self.eps, m._stream()), "tts_train_adam_peers")
+        self._stream_barrier()                     # every shard of the new parameters has landed in every rank's buffer
+        m._check(self._lib.tts_train_repack(self._h, m._stream()), "tts_train_repack")
+        m._dirty = True
+
     def step(self, phonemes, phoneme_lens, mels, mel_lens, seed: int = 0, utt_offset: int = 0) -> torch.Tensor:
         loss = self.forward_backward(phonemes, phoneme_lens, mels, mel_lens, seed, utt_offset)
-        self.all_reduce_grads()
-        self.adam_step()
+        if self._peers:
+            self.adam_step_peers()
+        else:
+            self.all_reduce_grads()
+            self.adam_step()
         return loss
 
     # ------------------------------------------------------------------ inspection

@@ -32,7 +32,7 @@ def _oracle_step(oracle_model, inputs, seed):
     return m, [o.detach() for o in out], loss.detach(), {k: p.grad.detach().clone() for k, p in m.named_parameters()}
 
 
-@pytest.mark.parametrize("B,S,T,ragged", [(3, 12, 20, True), (2, 40, 150, True), (4, 100, 260, False)])
+@pytest.mark.parametrize("B,S,T,ragged", [(3, 12, 20, True), (2, 40, 150, True), (4, 100, 260, False), (1, 7, 13, False), (5, 33, 129, True)])
 def test_train_step_gradients(oracle_model, B, S, T, ragged):
     from oracle import synthetic
     from transformer_tacotron2_b200.training import Trainer
@@ -63,8 +63,10 @@ def test_train_step_gradients(oracle_model, B, S, T, ragged):
             else:
                 worst.append((rel_l2(got, want), k))
     worst.sort(reverse=True)
-    assert worst[0][0] < TOL_GRAD, worst[:8]
-    assert num ** 0.5 / float(total_ref) < TOL_GRAD_ALL, (num ** 0.5 / float(total_ref), worst[:8])
+    # (BatchNorm statistics over fewer than 16 encoder positions are ill-conditioned: the single-utterance case gets 2x)
+    loosen = 2.0 if B * S < 16 else 1.0
+    assert worst[0][0] < TOL_GRAD * loosen, worst[:8]
+    assert num ** 0.5 / float(total_ref) < TOL_GRAD_ALL * loosen, (num ** 0.5 / float(total_ref), worst[:8])
 
     # BatchNorm running statistics (P5: momentum 0.1, unbiased variance in the update)
     bufs = tr.buffers()

@@ -191,20 +191,17 @@ def test_peer_adam_kernel_world1_equals_plain_adam(oracle_model):
     from oracle import synthetic
     from transformer_tacotron2_b200.training import Trainer
     inputs = synthetic.make_inputs(2, 12, 20, 3, True)
-    res = []
-    for fused in (False, True):
-        model = make_b200_model(oracle_model)
-        tr = Trainer(model, lr=1e-3)
-        tr.forward_backward(*inputs, seed=4)
-        if fused:
-            assert tr._lib.tts_train_set_peers(tr._h, 0, 1, None, None) == 0
-            model._check(tr._lib.tts_train_adam_peers(tr._h, 1e-3, 0.9, 0.98, 1e-9, model._stream()), "adam_peers")
-            model._check(tr._lib.tts_train_repack(tr._h, model._stream()), "repack")
-        else:
-            tr.adam_step()
-        res.append(torch.cat([v.flatten() for _, v in sorted(tr.parameters().items())]))
-    # two separate backward passes: their gradients differ in the last bits (atomic accumulation order), and the first Adam
-    # step is sign-like (lr * g / (|g| + eps)), so elements whose gradient is ~eps may legitimately differ by up to 2 * lr
-    diff = (res[0] - res[1]).abs()
-    assert float((diff > 1e-6).float().mean()) < 1e-3, float((diff > 1e-6).float().mean())
-    assert float(diff.max()) <= 2.1e-3
+    ma, mb = make_b200_model(oracle_model), make_b200_model(oracle_model)
+    ta, tb = Trainer(ma, lr=1e-3), Trainer(mb, lr=1e-3)
+    ta.forward_backward(*inputs, seed=4)
+    tb.flat_grads.copy_(ta.flat_grads)          # identical gradients (two backward passes differ in the last bits: atomics)
+    ta.adam_step()
+    assert tb._lib.tts_train_set_peers(tb._h, 0, 1, None, None) == 0
+    mb._check(tb._lib.tts_train_adam_peers(tb._h, 1e-3, 0.9, 0.98, 1e-9, mb._stream()), "adam_peers")
+    mb._check(tb._lib.tts_train_repack(tb._h, mb._stream()), "repack")
+    pa, pb = ta.parameters(), tb.parameters()
+    for k in pa:
+        assert torch.allclose(pa[k], pb[k], atol=1e-7, rtol=1e-6), k
+    # and the refreshed bf16 operand copies give the same next loss
+    la, lb = float(ta.forward_backward(*inputs, seed=5)), float(tb.forward_backward(*inputs, seed=5))
+    assert abs(la - lb) <= 1e-4 * abs(la), (la, lb)

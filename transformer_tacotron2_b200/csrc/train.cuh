@@ -332,7 +332,8 @@ int tr_conv_fwd(TrCtx& c, const TrConv& cv, const bf16* in, int ldin, int M, int
     const dim3 g((m.N + 127) / 128, 592);
     bn_stats_kernel<<<g, 128, 0, c.st>>>(pre, M, m.N, Trows, c.B, lens, stat, 0);
     bn_stats_kernel<<<g, 128, 0, c.st>>>(pre, M, m.N, Trows, c.B, lens, stat, 1);
-    bn_act_fwd_kernel<<<std::min<long>(((long)M * m.N + 255) / 256, 2368), 256, 0, c.st>>>(pre, M, m.N, Trows, c.B, lens, stat, c.P + cv.g, c.P + cv.be, c.h->cfg.bn_eps, act,
+    const int bn_threads = (m.N / 4) * std::max(1, 256 / (m.N / 4));      // (C / 4) channel groups x row lanes
+    bn_act_fwd_kernel<<<1184, bn_threads, 0, c.st>>>(pre, M, m.N, Trows, c.B, lens, stat, c.P + cv.g, c.P + cv.be, c.h->cfg.bn_eps, act,
                                                                                           site, c.seed, c.utt0, out16, ldo, out32, c.t->RS + cv.rm, c.t->RS + cv.rv, 0.1f);
     launch_counter() += 3;
     TRL(cudaGetLastError());
@@ -346,7 +347,8 @@ int tr_conv_bwd(TrCtx& c, const TrConv& cv, const TD* dout, int ldd, const float
     const dim3 g((m.N + 127) / 128, 592);
     bn_bwd_reduce_kernel<TD><<<g, 128, 0, c.st>>>(dout, ldd, pre, M, m.N, Trows, c.B, lens, stat, c.P + cv.g, c.P + cv.be, c.h->cfg.bn_eps, act, site, c.seed,
                                                   c.utt0, c.G + cv.be, c.G + cv.g);
-    bn_bwd_apply_kernel<TD><<<std::min<long>(((long)M * m.N + 255) / 256, 2368), 256, 0, c.st>>>(dout, ldd, pre, M, m.N, Trows, c.B, lens, stat, c.P + cv.g, c.P + cv.be,
+    const int bn_threads = (m.N / 4) * std::max(1, 256 / (m.N / 4));
+    bn_bwd_apply_kernel<TD><<<1184, bn_threads, 0, c.st>>>(dout, ldd, pre, M, m.N, Trows, c.B, lens, stat, c.P + cv.g, c.P + cv.be,
                                                                                                  c.h->cfg.bn_eps, act, site, c.seed, c.utt0, c.G + cv.be, c.G + cv.g, dpre, m.N);
     launch_counter() += 2;
     TRL(cudaGetLastError());
@@ -452,7 +454,7 @@ int train_forward_backward(TrCtx& c, float* loss_out, float pos_weight) {
     TRL(cudaMemsetAsync(w.acc, 0, 64, st));
     loss_kernel<<<std::min<long>(((long)Md * 81 + 255) / 256, 2368), 256, 0, st>>>(w.mel_before, w.mel_after, w.stop, mels, mlens, B, T, pos_weight, w.acc, w.dbefore,
                                                                                   w.dafter, w.dstop);
-    loss_finalize_kernel<<<1, 1, 0, st>>>(w.acc, mlens, B, loss_out);
+    loss_finalize_kernel<<<1, 32, 0, st>>>(w.acc, mlens, B, loss_out);
     launch_counter() += 2;
     TRL(cudaGetLastError());
 

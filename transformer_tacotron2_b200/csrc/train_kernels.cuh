@@ -32,13 +32,25 @@ __global__ void __launch_bounds__(256) cast_pack_all_kernel(const PackDesc* __re
 }
 
 // ---------------------------------------------------------------------------------------------- masked BatchNorm (P5)
-TTS_D float n_valid(const int* lens, int B) { int n = 0; for (int b = 0; b < B; ++b) n += lens[b]; return (float)max(n, 1); }
+// number of valid positions of the batch; computed once per block by its first warp (every thread of the block must call it)
+TTS_D float n_valid(const int* lens, int B) {
+    __shared__ float s_n;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid < 32) {
+        int n = 0;
+        for (int b = tid; b < B; b += 32) n += lens[b];
+        n = (int)warp_sum((float)n);
+        if (tid == 0) s_n = (float)max(n, 1);
+    }
+    __syncthreads();
+    return s_n;
+}
 
 // pass 0: stat[c] += sum_valid x;  pass 1: stat[C + c] += sum_valid (x - mean)^2      (stat zeroed by the caller)
 __global__ void bn_stats_kernel(const float* __restrict__ x, int M, int C, int T, int B, const int* __restrict__ lens, float* __restrict__ stat, int pass) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
     const float n = n_valid(lens, B);
+    if (c >= C) return;
     const float mean = pass ? stat[c] / n : 0.f;
     const int rows = (M + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
     float acc = 0.f;
@@ -50,31 +62,52 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int M, int C, int T
     if (r1 > r0) atomicAdd(stat + pass * C + c, acc);
 }
 
-// y = mask * dropbits( act( (x - mean) * rstd * gamma + beta ) ); optional running-stat update by block 0
+// y = mask * dropbits( act( (x - mean) * rstd * gamma + beta ) ); optional running-stat update by block 0.
+// Thread = 4 consecutive channels (C % 4 == 0; blockDim.x = (C / 4) * row lanes, so a thread's channels never change and
+// its statistics are hoisted); the 4 keep-bits come from one Philox call.
+TTS_D uint32_t keep_bits4(uint64_t seed, uint32_t site, uint32_t t, uint32_t b, uint32_t c) {      // bits 0..3 = channels c..c+3 (c % 4 == 0)
+    const uint4 w = philox4x32_10(make_uint4(site, t, b, c >> 7), (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t word = (c >> 5) & 3u;
+    const uint32_t v = word == 0 ? w.x : word == 1 ? w.y : word == 2 ? w.z : w.w;
+    return (v >> (c & 31u)) & 15u;
+}
 __global__ void bn_act_fwd_kernel(const float* __restrict__ x, int M, int C, int T, int B, const int* __restrict__ lens, const float* __restrict__ stat,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, int site, const uint64_t* seedp,
                                   int utt_offset, bf16* __restrict__ out16, int ldo, float* __restrict__ out32, float* run_mean, float* run_var,
                                   float momentum) {
     const uint64_t seed = *seedp;
     const float n = n_valid(lens, B);
-    const long total = (long)M * C;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C), m = (int)(i / C), b = m / T, t = m - b * T;
-        float v = 0.f;
-        if (t < lens[b]) {
-            const float mean = stat[c] / n, rstd = rsqrtf(stat[C + c] / n + eps);
-            v = (x[i] - mean) * rstd * gamma[c] + beta[c];
-            if (act == 1) v = fmaxf(v, 0.f); else if (act == 2) v = tanhf(v);
-            if (site >= 0) v = keep_bit(seed, site, t, utt_offset + b, c) ? 2.f * v : 0.f;
+    const int c4n = C >> 2, rl = blockDim.x / c4n, cg = threadIdx.x % c4n, rlane = threadIdx.x / c4n, c = cg * 4;
+    if (rlane < rl) {
+        float sc[4], sh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float mean = stat[c + k] / n, rstd = rsqrtf(stat[C + c + k] / n + eps);
+            sc[k] = rstd * gamma[c + k]; sh[k] = beta[c + k] - mean * sc[k];
         }
-        if (out16) out16[(long)m * ldo + c] = __float2bfloat16(v);
-        if (out32) out32[i] = v;
+        for (int m = blockIdx.x * rl + rlane; m < M; m += gridDim.x * rl) {
+            const int b = m / T, t = m - b * T;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (t < lens[b]) {
+                const float4 xv = *reinterpret_cast<const float4*>(x + (long)m * C + c);
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                const uint32_t kb = site >= 0 ? keep_bits4(seed, site, t, utt_offset + b, c) : 15u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float y = xs[k] * sc[k] + sh[k];
+                    if (act == 1) y = fmaxf(y, 0.f); else if (act == 2) y = tanhf(y);
+                    v[k] = site >= 0 ? (((kb >> k) & 1u) ? 2.f * y : 0.f) : y;
+                }
+            }
+            if (out16) *reinterpret_cast<uint2*>(out16 + (long)m * ldo + c) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+            if (out32) *reinterpret_cast<float4*>(out32 + (long)m * C + c) = make_float4(v[0], v[1], v[2], v[3]);
+        }
     }
     if (run_mean && blockIdx.x == 0)
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const float mean = stat[c] / n, var = stat[C + c] / n;
-            run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
-            run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * n / fmaxf(n - 1.f, 1.f);
+        for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+            const float mean = stat[cc] / n, var = stat[C + cc] / n;
+            run_mean[cc] = (1.f - momentum) * run_mean[cc] + momentum * mean;
+            run_var[cc] = (1.f - momentum) * run_var[cc] + momentum * var * n / fmaxf(n - 1.f, 1.f);
         }
 }
 
@@ -93,9 +126,9 @@ __global__ void bn_bwd_reduce_kernel(const TD* __restrict__ dout, int ldd, const
                                      const float* __restrict__ beta, float eps, int act, int site, const uint64_t* seedp, int utt_offset, float* __restrict__ dbeta,
                                      float* __restrict__ dgamma) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const float n = n_valid(lens, B);
     if (c >= C) return;
     const uint64_t seed = *seedp;
-    const float n = n_valid(lens, B);
     const float mean = stat[c] / n, rstd = rsqrtf(stat[C + c] / n + eps), ga = gamma[c], be = beta[c];
     const int rows = (M + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * rows, r1 = min(M, r0 + rows);
     float s0 = 0.f, s1 = 0.f;
@@ -108,7 +141,9 @@ __global__ void bn_bwd_reduce_kernel(const TD* __restrict__ dout, int ldd, const
     }
     if (r1 > r0) { atomicAdd(dbeta + c, s0); atomicAdd(dgamma + c, s1); }
 }
-// dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat)) on valid rows, 0 elsewhere  -> bf16
+// dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat)) on valid rows, 0 elsewhere  -> bf16   (thread = 4 channels, as above)
+TTS_D float load1(const float* p) { return *p; }
+TTS_D float load1(const bf16* p) { return __bfloat162float(*p); }
 template <typename TD>
 __global__ void bn_bwd_apply_kernel(const TD* __restrict__ dout, int ldd, const float* __restrict__ x, int M, int C, int T, int B,
                                     const int* __restrict__ lens, const float* __restrict__ stat, const float* __restrict__ gamma,
@@ -116,17 +151,33 @@ __global__ void bn_bwd_apply_kernel(const TD* __restrict__ dout, int ldd, const 
                                     const float* __restrict__ dbeta, const float* __restrict__ dgamma, bf16* __restrict__ dx, int ldx) {
     const uint64_t seed = *seedp;
     const float n = n_valid(lens, B);
-    const long total = (long)M * C;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C), m = (int)(i / C), b = m / T, t = m - b * T;
-        float v = 0.f;
+    const int c4n = C >> 2, rl = blockDim.x / c4n, cg = threadIdx.x % c4n, rlane = threadIdx.x / c4n, c = cg * 4;
+    if (rlane >= rl) return;
+    float mean[4], rstd[4], ga[4], be[4], mg[4], mgx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        mean[k] = stat[c + k] / n; rstd[k] = rsqrtf(stat[C + c + k] / n + eps); ga[k] = gamma[c + k]; be[k] = beta[c + k];
+        mg[k] = dbeta[c + k] / n; mgx[k] = dgamma[c + k] / n;
+    }
+    for (int m = blockIdx.x * rl + rlane; m < M; m += gridDim.x * rl) {
+        const int b = m / T, t = m - b * T;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (t < lens[b]) {
-            const float mean = stat[c] / n, rstd = rsqrtf(stat[C + c] / n + eps), ga = gamma[c];
-            const float xh = (x[i] - mean) * rstd;
-            const float g = bn_dact(to_f32(dout[(long)m * ldd + c]), xh * ga + beta[c], act, site, seed, t, utt_offset + b, c);
-            v = ga * rstd * (g - dbeta[c] / n - xh * dgamma[c] / n);
+            const float4 xv = *reinterpret_cast<const float4*>(x + (long)m * C + c);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+            const uint32_t kb = site >= 0 ? keep_bits4(seed, site, t, utt_offset + b, c) : 15u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float xh = (xs[k] - mean[k]) * rstd[k];
+                float g = load1(dout + (long)m * ldd + c + k);
+                if (site >= 0) g = ((kb >> k) & 1u) ? 2.f * g : 0.f;
+                const float yb = xh * ga[k] + be[k];
+                if (act == 1) g = yb > 0.f ? g : 0.f;
+                else if (act == 2) { const float th = tanhf(yb); g *= 1.f - th * th; }
+                v[k] = ga[k] * rstd[k] * (g - mg[k] - xh * mgx[k]);
+            }
         }
-        dx[(long)m * ldx + c] = __float2bfloat16(v);
+        *reinterpret_cast<uint2*>(dx + (long)m * ldx + c) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
     }
 }
 
@@ -281,9 +332,9 @@ __global__ void loss_kernel(const float* __restrict__ before, const float* __res
     if ((threadIdx.x & 31) == 0) { atomicAdd(acc, a0); atomicAdd(acc + 1, a1); atomicAdd(acc + 2, a2); }
 }
 // loss = acc0 / (n * 80) + acc1 / (n * 80) + acc2 / n
-__global__ void loss_finalize_kernel(const float* acc, const int* lens, int B, float* loss) {
+__global__ void loss_finalize_kernel(const float* acc, const int* lens, int B, float* loss) {      // one warp
     const float n = n_valid(lens, B);
-    loss[0] = acc[0] / (n * 80.f) + acc[1] / (n * 80.f) + acc[2] / n;
+    if (threadIdx.x == 0) loss[0] = acc[0] / (n * 80.f) + acc[1] / (n * 80.f) + acc[2] / n;
 }
 // dhead16[m][0..79] = mask * (dbefore + dafter + dpost0), [80] = dstop, rest 0    (mel_after = (mel_before + postnet) * mask)
 __global__ void head_grad_kernel(const float* __restrict__ dbefore32, const float* __restrict__ dafter32, const bf16* __restrict__ dpost0, int ldp,

@@ -67,7 +67,8 @@ def test_conv5(lib, B, T, Cin, Cout):
 
 
 @pytest.mark.parametrize("B,Lq,Lk,causal", [(2, 100, 100, 0), (1, 1, 1, 0), (2, 63, 65, 0), (2, 129, 129, 1),
-                                             (1, 400, 400, 1), (2, 200, 37, 0), (1, 64, 300, 0)])
+                                             (1, 400, 400, 1), (2, 200, 37, 0), (1, 64, 300, 0), (1, 127, 127, 1), (2, 128, 128, 0),
+                                             (1, 257, 129, 0), (1, 1600, 1600, 1), (3, 800, 100, 0)])
 def test_attention(lib, B, Lq, Lk, causal):
     H = 8
     g = torch.Generator().manual_seed(Lq * 7 + Lk)
@@ -93,7 +94,8 @@ def test_attention(lib, B, Lq, Lk, causal):
 
 
 @pytest.mark.parametrize("B,Lq,Lk,causal", [(2, 100, 100, 0), (2, 129, 129, 1), (1, 400, 400, 1), (2, 200, 37, 0), (1, 64, 300, 0),
-                                             (2, 260, 260, 1)])
+                                             (2, 260, 260, 1), (1, 1, 1, 0), (1, 127, 127, 1), (2, 128, 128, 0), (1, 257, 129, 0),
+                                             (1, 800, 800, 1), (3, 800, 100, 0)])
 def test_attention_backward(lib, B, Lq, Lk, causal):
     """dQ / dK / dV of the tcgen05 backward kernel against torch autograd (fp32) on the same bf16 inputs."""
     H = 8
@@ -125,6 +127,9 @@ def test_attention_backward(lib, B, Lq, Lk, causal):
     assert torch.allclose(lse.cpu(), ref_lse, atol=2e-2, rtol=1e-3)
     for name, got, want in (("dQ", dQ, qf.grad), ("dK", dK, kf.grad), ("dV", dV, vf.grad)):
         got = got.float().cpu()
+        if float(want.norm()) < 1e-6:                         # a single key: softmax = 1, dS = 0, so dQ = dK = 0 exactly
+            assert float(got.norm()) < 1e-3, (name, float(got.norm()))
+            continue
         err = float((got - want).norm() / want.norm())
         assert err < 2e-2, (name, err)                       # bf16 P / dS operands: ~1e-2 relative
         assert torch.allclose(got, want, atol=6e-2, rtol=6e-2), (name, float((got - want).abs().max()))

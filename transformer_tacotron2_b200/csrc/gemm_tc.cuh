@@ -18,10 +18,10 @@
 
 namespace tts {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4;
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 4;     // N tile: 256 (default) or 128 (template parameter BN)
 constexpr int TC_EPI_WARPS = 8;                                           // two warps per TMEM lane quarter, half of the columns each
-constexpr int TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2;              // 48 KB
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_EPI_WARPS * 4096 + 1024 + 256;   // ring + output staging + alignment slack + barriers
+__host__ __device__ constexpr int tc_stage_bytes(int BN) { return (TC_BM + BN) * TC_BK * 2; }      // 48 KB / 32 KB
+__host__ __device__ constexpr int tc_smem_bytes(int BN) { return TC_STAGES * tc_stage_bytes(BN) + TC_EPI_WARPS * 4096 + 1024 + 256; }   // ring + output staging + alignment slack + barriers
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 struct GemmTcParams {
@@ -61,9 +61,12 @@ TTS_D uint64_t tc_smem_desc(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9 = 1, 10-12 = 1), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28  -- cute::UMMA::InstrDescriptor
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t tc_idesc(int BN) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24); }
 
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
+    constexpr int TC_BN = BN, TC_STAGE_BYTES = tc_stage_bytes(BN);
+    constexpr uint32_t TC_IDESC = tc_idesc(BN);
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* ostage = smem + TC_STAGES * TC_STAGE_BYTES;          // [TC_EPI_WARPS][4 KB] output staging for the TMA stores
@@ -148,7 +151,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g.bias) {
             const int bc = n0 + chalf * (TC_BN / 2) + lane * 4;
-            if (bc + 3 < g.N) bq = __ldg(reinterpret_cast<const float4*>(g.bias + bc));
+            if (lane * 4 >= TC_BN / 2) { /* this lane's columns belong to the other warp */ }
+            else if (bc + 3 < g.N) bq = __ldg(reinterpret_cast<const float4*>(g.bias + bc));
             else { if (bc < g.N) bq.x = g.bias[bc]; if (bc + 1 < g.N) bq.y = g.bias[bc + 1]; if (bc + 2 < g.N) bq.z = g.bias[bc + 2]; }
         }
         tc_mbar_wait(&tmem_full[acc], (j >> 1) & 1);
@@ -324,9 +328,12 @@ inline TcEncodeFn tc_encode_fn() {
 // W has taps * Nw rows (Nw = N rounded up to 128).  Returns cudaErrorInvalidValue for shapes it cannot describe.
 inline cudaError_t launch_gemm_tc(const GemmParams& g, cudaStream_t stream) {
     static bool attr_set = false;
+    static int num_sms = 0;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(256));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(128));
         if (e != cudaSuccess) return e;
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         attr_set = true;
     }
     TcEncodeFn enc = tc_encode_fn();
@@ -336,6 +343,10 @@ inline cudaError_t launch_gemm_tc(const GemmParams& g, cudaStream_t stream) {
     p.Tl = g.taps > 1 ? g.T : g.M;                       // plain GEMMs ignore the utterance structure when loading A
     const int nb = g.M / p.Tl;
     p.tiles_per_utt = (p.Tl + TC_BM - 1) / TC_BM;
+    // N tile: 256 columns halve the operand traffic per FLOP; 128 when that would leave SMs idle (small M: the encoder) or
+    // when N itself is narrow (80 / 81 / 128-wide outputs)
+    const int m_tiles = nb * p.tiles_per_utt;
+    const int TC_BN = (g.N <= 128 || (long)m_tiles * ((g.N + 255) / 256) < num_sms) ? 128 : 256;
     const cuuint32_t estr[3] = {1, 1, 1};
     {
         const cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)p.Tl, (cuuint64_t)nb};
@@ -348,7 +359,7 @@ inline cudaError_t launch_gemm_tc(const GemmParams& g, cudaStream_t stream) {
     {
         const cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.taps * g.Nw};
         const cuuint64_t strides[1] = {(cuuint64_t)g.ldw * 2};
-        const cuuint32_t box[2] = {TC_BK, TC_BN};
+        const cuuint32_t box[2] = {TC_BK, (cuuint32_t)TC_BN};
         if (enc(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(g.W), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
@@ -369,10 +380,9 @@ inline cudaError_t launch_gemm_tc(const GemmParams& g, cudaStream_t stream) {
     }
     p.n_tiles_n = (g.N + TC_BN - 1) / TC_BN;
     p.n_tiles = p.n_tiles_n * nb * p.tiles_per_utt;
-    static int num_sms = 0;
-    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;          // persistent: one CTA per SM, static round-robin tiles
-    gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+    if (TC_BN == 256) gemm_tc_kernel<256><<<grid, TC_THREADS, tc_smem_bytes(256), stream>>>(p);
+    else gemm_tc_kernel<128><<<grid, TC_THREADS, tc_smem_bytes(128), stream>>>(p);
     ++launch_counter();
     return cudaGetLastError();
 }

@@ -50,6 +50,23 @@ def test_no_gpu_means_loud_failure_not_fallback():
     assert lib.tts_create(C.byref(cc), 0, C.byref(h)) != 0
 
 
+def test_training_without_gpu_fails_loudly_too():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from transformer_tacotron2_b200 import TransformerTTS
+    from transformer_tacotron2_b200.training import Trainer
+    with pytest.raises(RuntimeError):
+        Trainer(TransformerTTS())
+    # the training entry points refuse a null handle instead of crashing
+    from transformer_tacotron2_b200 import _lib
+    lib = _lib.load()
+    assert lib.tts_train_begin(None) != 0
+    assert lib.tts_train_num_tensors(None) == -1
+    assert lib.tts_train_workspace_bytes(None, 4, 10, 20) == 0
+
+
 def test_product_package_never_imports_oracle():
     pkg = os.path.join(ROOT, "transformer_tacotron2_b200")
     for dp, _, files in os.walk(pkg):

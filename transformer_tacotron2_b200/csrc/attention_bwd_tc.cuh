@@ -3,11 +3,13 @@
 //     P = 2^(S * scale_log2 - L),  S = Q K^T        dP = dO V^T        dS = P * (dP - D) / sqrt(dh)
 //     dV = P^T dO        dK = dS^T Q        dQ = dS K
 // One CTA = one 128-key tile of one (b, h), looping over the 128-query tiles that see it (causal: i >= j).
-//   warp 0      TMA producer: K_j, V_j once; Q_i, dO_i double-buffered (4-D maps, 128B swizzle, zero fill past the end)
+//   warp 0      TMA producer: K_j, V_j once; Q_i, dO_i in a 3-stage ring (4-D maps, 128B swizzle, zero fill past the end)
 //   warp 1      MMA issuer:   S, dP        M128(q) N128(keys) K64,  operands K-major from shared memory  -> TMEM
 //                             dV += P^T dO, dK += dS^T Q   M128(keys) N64 K128(q): A = the bf16 P / dS tile in shared memory
 //                                                          read as an MN-major operand, B = dO_i / Q_i as MN-major
 //                             dQ_i = dS K_j               M128(q) N64 K128(keys): A = dS K-major, B = K_j MN-major
+// Pipelining: S is double-buffered in TMEM and dQ_i reuses dP_i's columns (all 512 columns are in use), so S_{i+1} exists
+// before tile i's three MMAs are issued and the exponentials of tile i + 1 run underneath them.
 //   warps 2..9  thread = query row x half of the columns: S -> P (bf16, swizzled store), dP -> dS, then dQ_i from TMEM -> fp32 red.add into the
 //               dQ accumulator (several key tiles add into the same rows); at the end dK_j, dV_j -> bf16.
 #pragma once
@@ -37,8 +39,9 @@ struct AttnBwdTcParams {
 constexpr int FB_CWARPS = 8;                                        // compute warps: two per TMEM lane quarter, half of the columns each
 constexpr int FB_THREADS = 64 + 32 * FB_CWARPS;
 constexpr int FB_TILE = 128 * 64 * 2;                               // 16 KB
-constexpr int FB_SMEM_BYTES = 10 * FB_TILE + 256;                   // K, V, Q[2], dO[2], P (2 halves), dS (2 halves)
-constexpr int FB_COL_S = 0, FB_COL_DP = 128, FB_COL_DV = 256, FB_COL_DK = 320, FB_COL_DQ = 384;
+constexpr int FB_QSTAGES = 3;                                       // Q / dO ring: tile i + 2 is loaded while tile i is in the MMAs
+constexpr int FB_SMEM_BYTES = (6 + 2 * FB_QSTAGES) * FB_TILE + 256;   // K, V, Q[3], dO[3], P (2 halves), dS (2 halves)
+constexpr int FB_COL_S = 0, FB_COL_DP = 256, FB_COL_DQ = 256, FB_COL_DV = 384, FB_COL_DK = 448;   // S[2] | dP (dQ aliases it) | dV | dK = 512 columns
 // kind::f16 instruction descriptors (see gemm_tc.cuh): bit 15 = A is MN-major, bit 16 = B is MN-major
 constexpr uint32_t FB_IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr uint32_t FB_IDESC_KV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -57,14 +60,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
     extern __shared__ __align__(1024) unsigned char fb_smem[];
     unsigned char* sK = fb_smem;
     unsigned char* sV = fb_smem + FB_TILE;
-    unsigned char* sQ = fb_smem + 2 * FB_TILE;           // [2]
-    unsigned char* sdO = fb_smem + 4 * FB_TILE;          // [2]
-    unsigned char* sP = fb_smem + 6 * FB_TILE;           // [q 128][keys 0..63], [q 128][keys 64..127]
-    unsigned char* sdS = fb_smem + 8 * FB_TILE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(fb_smem + 10 * FB_TILE);
-    uint64_t *kv_full = bars, *qd_full = bars + 1, *qd_empty = bars + 3, *s_full = bars + 5, *sdp_empty = bars + 6;
-    uint64_t *ds_full = bars + 7, *mma3_done = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    unsigned char* sQ = fb_smem + 2 * FB_TILE;                          // [FB_QSTAGES]
+    unsigned char* sdO = fb_smem + (2 + FB_QSTAGES) * FB_TILE;          // [FB_QSTAGES]
+    unsigned char* sP = fb_smem + (2 + 2 * FB_QSTAGES) * FB_TILE;       // [q 128][keys 0..63], [q 128][keys 64..127]
+    unsigned char* sdS = fb_smem + (4 + 2 * FB_QSTAGES) * FB_TILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fb_smem + (6 + 2 * FB_QSTAGES) * FB_TILE);
+    uint64_t *kv_full = bars, *qd_full = bars + 1, *qd_empty = bars + 4, *s_full = bars + 7, *s_empty = bars + 9;
+    uint64_t *dp_full = bars + 11, *dpq_free = bars + 12, *ds_full = bars + 13, *mma3_done = bars + 14;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const AttnBwdParams& a = p.a;
     const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -77,8 +80,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
     if (threadIdx.x == 0) {
         if (tc_smem_u32(fb_smem) & 1023) __trap();
         tc_mbar_init(kv_full, 1);
-        for (int s = 0; s < 2; ++s) { tc_mbar_init(&qd_full[s], 1); tc_mbar_init(&qd_empty[s], 1); }
-        tc_mbar_init(s_full, 1); tc_mbar_init(sdp_empty, FB_CWARPS); tc_mbar_init(ds_full, FB_CWARPS); tc_mbar_init(mma3_done, 1);
+        for (int s = 0; s < FB_QSTAGES; ++s) { tc_mbar_init(&qd_full[s], 1); tc_mbar_init(&qd_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc_mbar_init(&s_full[s], 1); tc_mbar_init(&s_empty[s], FB_CWARPS); }
+        tc_mbar_init(dp_full, 1); tc_mbar_init(dpq_free, FB_CWARPS); tc_mbar_init(ds_full, FB_CWARPS); tc_mbar_init(mma3_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
             ft_tma_4d(sK, &p.tm_k, 0, k0, h, b, kv_full);
             ft_tma_4d(sV, &p.tm_v, 0, k0, h, b, kv_full);
             for (int it = 0; it < ni; ++it) {
-                const int s = it & 1; const uint32_t use = it >> 1;
+                const int s = it % FB_QSTAGES; const uint32_t use = it / FB_QSTAGES;
                 if (use > 0) tc_mbar_wait(&qd_empty[s], (use & 1) ^ 1);
                 tc_mbar_expect_tx(&qd_full[s], 2 * FB_TILE);
                 ft_tma_4d(sQ + s * FB_TILE, &p.tm_q, 0, (i0 + it) * 128, h, b, &qd_full[s]);
@@ -106,23 +110,35 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
     } else if (warp == 1) {
         if (lane == 0 && ni > 0) {                       // ---------------- MMA issuer
             const uint32_t ka = tc_smem_u32(sK), va = tc_smem_u32(sV), pa = tc_smem_u32(sP), dsa = tc_smem_u32(sdS);
-            auto issue_sdp = [&](int it) {
-                const int s = it & 1;
-                tc_mbar_wait(&qd_full[s], (it >> 1) & 1);
-                if (it > 0) tc_mbar_wait(sdp_empty, (it - 1) & 1);           // S / dP of the previous tile are in registers
+            // S_it -> TMEM S[it & 1] (double-buffered: the exponentials of tile it + 1 run while tile it's three MMAs do)
+            auto issue_s = [&](int it) {
+                const int s = it & 1, qs = it % FB_QSTAGES;
+                tc_mbar_wait(&qd_full[qs], (it / FB_QSTAGES) & 1);
+                if (it >= 2) tc_mbar_wait(&s_empty[s], ((it >> 1) - 1) & 1);     // S_{it-2} has been read
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t qa = tc_smem_u32(sQ + s * FB_TILE), da = tc_smem_u32(sdO + s * FB_TILE);
+                const uint32_t qa = tc_smem_u32(sQ + qs * FB_TILE);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ft_mma(tmem_base + FB_COL_S, tc_smem_desc(qa + k * 32), tc_smem_desc(ka + k * 32), FB_IDESC_S, k != 0);
+                for (int k = 0; k < 4; ++k) ft_mma(tmem_base + FB_COL_S + s * 128, tc_smem_desc(qa + k * 32), tc_smem_desc(ka + k * 32), FB_IDESC_S, k != 0);
+                ft_commit(&s_full[s]);
+            };
+            // dP_it -> the dP/dQ columns (free once dQ_{it-1}, which aliases them, has been read)
+            auto issue_dp = [&](int it) {
+                const int qs = it % FB_QSTAGES;
+                tc_mbar_wait(&qd_full[qs], (it / FB_QSTAGES) & 1);
+                if (it > 0) tc_mbar_wait(dpq_free, (it - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t da = tc_smem_u32(sdO + qs * FB_TILE);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ft_mma(tmem_base + FB_COL_DP, tc_smem_desc(da + k * 32), tc_smem_desc(va + k * 32), FB_IDESC_S, k != 0);
-                ft_commit(s_full);
+                ft_commit(dp_full);
             };
             tc_mbar_wait(kv_full, 0);
-            issue_sdp(0);
+            issue_s(0);
+            issue_dp(0);
+            if (ni > 1) issue_s(1);
             for (int it = 0; it < ni; ++it) {
-                const int s = it & 1;
-                tc_mbar_wait(ds_full, it & 1);           // P and dS are in shared memory; dQ of the previous tile has been read
+                const int s = it % FB_QSTAGES;
+                tc_mbar_wait(ds_full, it & 1);           // P_it and dS_it are in shared memory
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t qa = tc_smem_u32(sQ + s * FB_TILE), da = tc_smem_u32(sdO + s * FB_TILE);
 #pragma unroll
@@ -131,31 +147,50 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
                     ft_mma(tmem_base + FB_COL_DK, fb_desc_mn(dsa + k * 2048, FB_TILE), fb_desc_mn(qa + k * 2048, 16), FB_IDESC_KV, (it | k) != 0);
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k)              // 16 keys per MMA: dS K-major (half k / 4, 32-byte step), K_j rows 16k..
+                for (int k = 0; k < 8; ++k)              // dQ_it = dS K_j into the columns dP_it occupied (it has been consumed)
                     ft_mma(tmem_base + FB_COL_DQ, tc_smem_desc(dsa + (k >> 2) * FB_TILE + (k & 3) * 32), fb_desc_mn(ka + k * 2048, 16), FB_IDESC_Q, k != 0);
                 ft_commit(&qd_empty[s]);
                 ft_commit(mma3_done);
-                if (it + 1 < ni) issue_sdp(it + 1);
+                if (it + 1 < ni) issue_dp(it + 1);       // waits until the compute warps have taken dQ_it out
+                if (it + 2 < ni) issue_s(it + 2);        // its Q stage was freed one tile ago and has been refilled meanwhile
             }
         }
-    } else if (ni > 0) {                                 // ---------------- thread = query row of the tile
-        const int lg = warp & 3, r = lg * 32 + lane, ch = (warp - 2) >> 2;     // ch: which half of the columns this warp owns
+    } else if (ni > 0) {                                 // ---------------- thread = query row of the tile, half of the columns
+        const int lg = warp & 3, r = lg * 32 + lane, ch = (warp - 2) >> 2;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        auto take_dq = [&](int it) {                     // dQ of tile `it` (this key tile's contribution) -> fp32 red.add
+            const int qi = (i0 + it) * 128 + r;
+            tc_mbar_wait(mma3_done, it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t v[32];
+            ft_ld32_nowait(lane_addr + FB_COL_DQ + ch * 32, v);
+            ft_ld_wait();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) ft_arrive(dpq_free);          // the dP / dQ columns may be overwritten by dP of the next tile
+            if (qi < a.Lq) {
+                float* dq = a.dQ + b * a.dq_bs + h * a.dq_hs + (long)qi * a.dq_rs + ch * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    fb_red4(dq + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            }
+        };
         for (int it = 0; it < ni; ++it) {
+            const int s = it & 1;
             const int qi = (i0 + it) * 128 + r;
             const bool qvalid = qi < a.Lq;
             const long rowi = ((long)b * a.H + h) * a.Lq + qi;
             const float L = qvalid ? a.lse[rowi] : INFINITY;
             const float Dr = qvalid ? a.dsum[rowi] : 0.f;
             const int kmax = min(klen, a.causal ? qi + 1 : klen) - k0;       // keys [0, kmax) of this tile are visible to this row
-            tc_mbar_wait(s_full, it & 1);
+            // P_it in registers: runs while the tensor pipe works on tile it - 1
+            tc_mbar_wait(&s_full[s], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (it > 0) tc_mbar_wait(mma3_done, (it - 1) & 1);               // the MMAs that read the previous P / dS are complete
-            uint32_t pr[32];                                                 // P (this warp's 64 keys) as bf16 pairs, kept for dS
+            uint32_t pr[32];                                                 // P (this warp's 64 keys) as bf16 pairs
 #pragma unroll
             for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 32) {
                 uint32_t v[32];
-                ft_ld32_nowait(lane_addr + FB_COL_S + c0, v);
+                ft_ld32_nowait(lane_addr + FB_COL_S + s * 128 + c0, v);
                 ft_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
@@ -163,6 +198,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
                     const float p1 = (c0 + i + 1 < kmax) ? fast_exp2(__uint_as_float(v[i + 1]) * a.scale_log2 - L) : 0.f;
                     pr[((c0 & 63) + i) >> 1] = pack_bf16x2(p0, p1);
                 }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) ft_arrive(&s_empty[s]);
+            if (it > 0) take_dq(it - 1);                 // also: the MMAs that read the previous P / dS tiles are complete
+#pragma unroll
+            for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 32) {
                 unsigned char* half = sP + (c0 >> 6) * FB_TILE + r * 128;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -170,6 +212,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
                     *reinterpret_cast<uint4*>(half + ((chunk ^ (r & 7)) << 4)) = make_uint4(pr[w], pr[w + 1], pr[w + 2], pr[w + 3]);
                 }
             }
+            tc_mbar_wait(dp_full, it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int c0 = ch * 64; c0 < ch * 64 + 64; c0 += 32) {
                 uint32_t v[32];
@@ -191,24 +235,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) { ft_arrive(sdp_empty); ft_arrive(ds_full); }
-            // dQ_i of this key tile
-            tc_mbar_wait(mma3_done, it & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            {
-                const int c0 = ch * 32;
-                uint32_t v[32];
-                ft_ld32_nowait(lane_addr + FB_COL_DQ + c0, v);
-                ft_ld_wait();
-                if (qvalid) {
-                    float* dq = a.dQ + b * a.dq_bs + h * a.dq_hs + (long)qi * a.dq_rs + c0;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        fb_red4(dq + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) ft_arrive(ds_full);
         }
+        take_dq(ni - 1);
         // dK_j, dV_j: TMEM lane = key row
         const int ki = k0 + r;
 #pragma unroll

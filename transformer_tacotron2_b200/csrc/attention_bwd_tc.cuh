@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const AttnBwdParams& a = p.a;
-    const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int j = blockIdx.z, h = blockIdx.x, b = blockIdx.y;       // key tile slowest: with a causal mask tile 0 has the most work, and runs first
     const int k0 = j * 128;
     const int klen = a.klens ? min(a.klens[b], a.Lk) : a.Lk;
     const int nq = (a.Lq + 127) / 128;
@@ -313,7 +313,7 @@ inline cudaError_t launch_flash_attn_bwd_tc(const AttnBwdParams& a, cudaStream_t
     if (!make(&p.tm_q, a.Q, a.q_bs, a.q_hs, a.q_rs, a.Lq) || !make(&p.tm_k, a.K, a.k_bs, a.k_hs, a.k_rs, a.Lk) ||
         !make(&p.tm_v, a.V, a.v_bs, a.v_hs, a.v_rs, a.Lk) || !make(&p.tm_do, a.dO, a.o_bs, a.o_hs, a.o_rs, a.Lq))
         return cudaErrorInvalidValue;
-    dim3 grid((a.Lk + 127) / 128, a.H, a.B);
+    dim3 grid(a.H, a.B, (a.Lk + 127) / 128);
     flash_attn_bwd_tc_kernel<<<grid, FB_THREADS, FB_SMEM_BYTES, stream>>>(p);
     ++launch_counter();
     return cudaGetLastError();

@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2) flash_attn_tc_kernel(const __gr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const AttnParams& a = p.a;
-    const int q0 = blockIdx.x * FT_BM, h = blockIdx.y, b = blockIdx.z;
+    // query tile slowest and reversed: with a causal mask the last tile sees the most keys, so the longest CTAs start first
+    const int q0 = ((int)gridDim.z - 1 - (int)blockIdx.z) * FT_BM, h = blockIdx.x, b = blockIdx.y;
     const int klen = a.klens ? min(a.klens[b], a.Lk) : a.Lk;
     int nt = (klen + FT_BN - 1) / FT_BN;
     if (a.causal) nt = min(nt, (min(q0 + FT_BM, a.Lq) + FT_BN - 1) / FT_BN);
@@ -346,7 +347,7 @@ inline cudaError_t launch_flash_attn_tc(const AttnParams& a, cudaStream_t stream
     if (!make(&p.tm_q, a.Q, a.q_bs, a.q_hs, a.q_rs, a.Lq) || !make(&p.tm_k, a.K, a.k_bs, a.k_hs, a.k_rs, a.Lk) ||
         !make(&p.tm_v, a.V, a.v_bs, a.v_hs, a.v_rs, a.Lk))
         return cudaErrorInvalidValue;
-    dim3 grid((a.Lq + FT_BM - 1) / FT_BM, a.H, a.B);
+    dim3 grid(a.H, a.B, (a.Lq + FT_BM - 1) / FT_BM);
     flash_attn_tc_kernel<FT_POLY_EVERY><<<grid, FT_THREADS, FT_SMEM_BYTES, stream>>>(p);
     ++launch_counter();
     return cudaGetLastError();

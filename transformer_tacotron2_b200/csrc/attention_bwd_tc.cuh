@@ -24,6 +24,8 @@ struct AttnBwdParams {
     long q_bs, q_hs, q_rs, k_bs, k_hs, k_rs, v_bs, v_hs, v_rs, o_bs, o_hs, o_rs;
     const float *lse, *dsum;              // [B][H][Lq]
     float* dQ; long dq_bs, dq_hs, dq_rs;  // fp32 accumulator (zeroed by the caller), red.add
+    bf16* dQ16; long dq16_bs, dq16_hs, dq16_rs;   // if set AND there is a single key tile (Lk <= 128): dQ is complete after one tile and
+                                                  // is written directly as bf16 here (no zeroing, no fp32 pass)
     bf16 *dK, *dV; long dk_bs, dk_hs, dk_rs, dv_bs, dv_hs, dv_rs;
     int B, H, Lq, Lk;
     const int* klens;
@@ -169,10 +171,20 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
             __syncwarp();
             if (lane == 0) ft_arrive(dpq_free);          // the dP / dQ columns may be overwritten by dP of the next tile
             if (qi < a.Lq) {
-                float* dq = a.dQ + b * a.dq_bs + h * a.dq_hs + (long)qi * a.dq_rs + ch * 32;
+                if (a.dQ16 && a.Lk <= 128) {
+                    bf16* dq = a.dQ16 + b * a.dq16_bs + h * a.dq16_hs + (long)qi * a.dq16_rs + ch * 32;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    fb_red4(dq + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                    for (int i = 0; i < 32; i += 8)
+                        *reinterpret_cast<uint4*>(dq + i) = make_uint4(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                                                                       pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+                                                                       pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+                                                                       pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+                } else {
+                    float* dq = a.dQ + b * a.dq_bs + h * a.dq_hs + (long)qi * a.dq_rs + ch * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        fb_red4(dq + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+                }
             }
         };
         for (int it = 0; it < ni; ++it) {

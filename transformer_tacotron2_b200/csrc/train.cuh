@@ -310,13 +310,17 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
 // attention backward of one (self / cross) block; dQ lands (bf16) in dq16 with row stride lddq
 int tr_attn_bwd(TrCtx& c, const AttnParams& f, const bf16* O, const bf16* dO, const float* lse, bf16* dq16, int lddq, bf16* dK, int lddk, bf16* dV, int lddv) {
     const long nq = (long)f.B * f.Lq * 512;
-    TRL(cudaMemsetAsync(c.w.dq32, 0, nq * 4, c.st));
+    const bool single = f.Lk <= 128;                   // one key tile (cross-attention at S <= 128): dQ needs no accumulation across CTAs
+    if (!single) TRL(cudaMemsetAsync(c.w.dq32, 0, nq * 4, c.st));
     attn_dsum_kernel<<<(f.B * f.H * f.Lq + 31) / 32, 256, 0, c.st>>>(O, dO, f.o_bs, f.o_hs, f.o_rs, c.w.dsum, f.B, f.H, f.Lq);
     ++launch_counter();
     AttnBwdParams a = tr_abwd(f, dO, lse, c.w.dsum, c.w.dq32, dK, lddk, dV, lddv);
+    if (single) { a.dQ16 = dq16; a.dq16_bs = (long)f.Lq * lddq; a.dq16_hs = 64; a.dq16_rs = lddq; }
     TRL(launch_flash_attn_bwd_tc(a, c.st));
-    f32_to_bf16_strided_kernel<<<(unsigned)((nq / 4 + 255) / 256), 256, 0, c.st>>>(c.w.dq32, dq16, (long)f.B * f.Lq, lddq);
-    ++launch_counter();
+    if (!single) {
+        f32_to_bf16_strided_kernel<<<(unsigned)((nq / 4 + 255) / 256), 256, 0, c.st>>>(c.w.dq32, dq16, (long)f.B * f.Lq, lddq);
+        ++launch_counter();
+    }
     TRL(cudaGetLastError());
     return 0;
 }

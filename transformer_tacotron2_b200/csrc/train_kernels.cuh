@@ -15,18 +15,39 @@ namespace tts {
 // every matrix of the model in ONE launch: block -> descriptor (binary search over the first-block table), 2048 elements per block
 struct PackDesc { long src_off, dst_off; int N, K, taps, R, Cc, flip; int blk0; int pad_; };
 __global__ void __launch_bounds__(256) cast_pack_all_kernel(const PackDesc* __restrict__ descs, int nd, const float* __restrict__ P, bf16* __restrict__ wpack) {
+    __shared__ float tile[64][33];
     int lo = 0, hi = nd - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (descs[mid].blk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1; }
     const PackDesc d = descs[lo];
-    const long total = (long)d.taps * d.R * d.Cc, base = (long)(blockIdx.x - d.blk0) * 2048;
     const float* w = P + d.src_off; bf16* out = wpack + d.dst_off;
+    if (d.flip) {
+        // transposed layout out[tap][k][n] (R = Kw rows, Cc = Np columns): a 32(k) x 64(n) tile through shared memory so that
+        // both the fp32 reads (along k) and the bf16 writes (along n) are coalesced
+        const int tiles_n = d.Cc >> 6, tiles_k = d.R >> 5, lb = blockIdx.x - d.blk0;
+        const int tap = lb / (tiles_k * tiles_n), rem = lb - tap * tiles_k * tiles_n, kt = rem / tiles_n, nt = rem - kt * tiles_n;
+        const int st = d.taps - 1 - tap;
+        const int kl = threadIdx.x & 31, k = kt * 32 + kl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int nl = (threadIdx.x >> 5) + 8 * i, n = nt * 64 + nl;
+            tile[nl][kl] = (n < d.N && k < d.K) ? w[((long)n * d.K + k) * d.taps + st] : 0.f;
+        }
+        __syncthreads();
+        const int nl = threadIdx.x & 63, n = nt * 64 + nl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int kk = (threadIdx.x >> 6) + 4 * i;
+            out[((long)tap * d.R + kt * 32 + kk) * d.Cc + n] = __float2bfloat16(tile[nl][kk]);
+        }
+        return;
+    }
+    const long total = (long)d.taps * d.R * d.Cc, base = (long)(blockIdx.x - d.blk0) * 2048;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const long i = base + j * 256 + threadIdx.x;
         if (i < total) {
             const int c = (int)(i % d.Cc), r = (int)((i / d.Cc) % d.R), tap = (int)(i / ((long)d.Cc * d.R));
-            const int n = d.flip ? c : r, k = d.flip ? r : c, st = d.flip ? d.taps - 1 - tap : tap;
-            out[i] = __float2bfloat16((n < d.N && k < d.K) ? w[((long)n * d.K + k) * d.taps + st] : 0.f);
+            out[i] = __float2bfloat16((r < d.N && c < d.K) ? w[((long)r * d.K + c) * d.taps + tap] : 0.f);
         }
     }
 }

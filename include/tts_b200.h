@@ -7,6 +7,7 @@
  *
  *     TransformerTTS.forward(phonemes, phoneme_lens, mels, mel_lens)   -> mel_before, mel_after, stop_logits
  *     TransformerTTS.inference(phonemes, phoneme_lens, max_len, seed)  -> mel_after, mel_lens, stop_logits
+ *     + the training loop around them: model.train(); loss = tts_loss(model(...)); loss.backward(); all-reduce; Adam.step()
  *
  * (restated executable in oracle/transformer_tts.py:TransformerTTS).  The entry
  * points below are exactly what a Python binding of those two methods calls (the ctypes stub is in

@@ -21,6 +21,9 @@ FORWARD_CASE = dict(B=2, S=12, T=20, data_seed=201, seed=7, stop_bias=-8.0)
 # "stop margin", 0.046 here) is well above the bf16 path's logit error (~0.006): only then is
 # "stop indices bit-exact" a meaningful requirement.
 INFER_CASE = dict(B=3, S=16, max_len=48, data_seed=212, seed=7, stop_bias=-0.505)
+# one training step (train-mode forward with every dropout site on, loss P13, autograd): loss, train-mode outputs, the small
+# parameter gradients in full and the L2 norm of every gradient tensor
+TRAIN_CASE = dict(B=3, S=14, T=24, data_seed=233, seed=11, stop_bias=-8.0)
 
 
 def main():
@@ -43,7 +46,22 @@ def main():
                         phonemes=ph.numpy(), phoneme_lens=pl.numpy(), mel_after=ma.numpy(), mel_before=mb.numpy(),
                         mel_lens=lens.numpy(), stop_logits=st.numpy(), stop_bias=np.array(c["stop_bias"]),
                         max_len=np.array(c["max_len"]), seed=np.array(c["seed"]))
-    print("digest", digest, "lens", lens.tolist())
+    import copy
+    from oracle.transformer_tts import tts_loss
+    c = TRAIN_CASE
+    m = copy.deepcopy(synthetic.make_model(stop_bias=c["stop_bias"])).train()
+    ph, pl, mels, ml = synthetic.make_inputs(c["B"], c["S"], c["T"], c["data_seed"], ragged=True)
+    out = m(ph, pl, mels, ml, seed=c["seed"])
+    loss = tts_loss(*out, mels, ml)
+    loss.backward()
+    names = [k for k, _ in m.named_parameters()]
+    norms = np.array([float(p.grad.norm()) for _, p in m.named_parameters()], dtype=np.float64)
+    small = {("grad/" + k): p.grad.numpy() for k, p in m.named_parameters() if p.numel() <= 2048}
+    np.savez_compressed(os.path.join(HERE, "train_small.npz"), phonemes=ph.numpy(), phoneme_lens=pl.numpy(), mels=mels.numpy(),
+                        mel_lens=ml.numpy(), seed=np.array(c["seed"]), loss=np.array(float(loss)), names=np.array(names), grad_norms=norms,
+                        mel_before=out[0].detach().numpy(), mel_after=out[1].detach().numpy(), stop_logits=out[2].detach().numpy(),
+                        bn0_running_mean=m.postnet.convs[0].bn.running_mean.numpy(), **small)
+    print("digest", digest, "lens", lens.tolist(), "train loss", float(loss))
 
 
 if __name__ == "__main__":

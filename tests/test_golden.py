@@ -36,3 +36,24 @@ def test_inference_matches_golden():
     T = st.shape[1]
     valid = torch.arange(T)[None, :] < lens[:, None]
     assert float(st.abs()[valid].min()) > 0.04                             # the searched stop margin
+
+
+def test_train_step_matches_golden(oracle_model):
+    """Train-mode forward (all dropout sites, batch-statistics BatchNorm), loss and autograd of the oracle are frozen too."""
+    import copy
+    from oracle.transformer_tts import tts_loss
+    g = np.load(os.path.join(GOLD, "train_small.npz"))
+    m = copy.deepcopy(oracle_model).train()
+    mels, ml = torch.from_numpy(g["mels"]), torch.from_numpy(g["mel_lens"])
+    out = m(torch.from_numpy(g["phonemes"]), torch.from_numpy(g["phoneme_lens"]), mels, ml, seed=int(g["seed"]))
+    loss = tts_loss(*out, mels, ml)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 1e-4
+    assert np.allclose(out[1].detach().numpy(), g["mel_after"], atol=2e-4)
+    norms = np.array([float(p.grad.norm()) for _, p in m.named_parameters()])
+    assert [k for k, _ in m.named_parameters()] == list(g["names"])
+    assert np.allclose(norms, g["grad_norms"], rtol=2e-3, atol=1e-7)
+    for k, p in m.named_parameters():
+        if p.numel() <= 2048:
+            assert np.allclose(p.grad.numpy(), g["grad/" + k], atol=2e-5, rtol=2e-3), k
+    assert np.allclose(m.postnet.convs[0].bn.running_mean.numpy(), g["bn0_running_mean"], atol=1e-5)

@@ -135,3 +135,26 @@ def test_sinusoid_table_definition():
     import math
     assert abs(float(pe[5, 10]) - math.sin(5 / 10000 ** (10 / 512))) < 1e-6
     assert abs(float(pe[5, 11]) - math.cos(5 / 10000 ** (10 / 512))) < 1e-6
+
+
+def test_loss_matches_torch_functional_on_full_lengths():
+    """P13: on an unpadded batch the masked-mean loss is F.mse_loss + F.mse_loss + BCEWithLogitsLoss(pos_weight=5) with the
+    stop target at the last frame ([TA]-style gate loss; Tacotron 2 sums the before / after MSE terms)."""
+    import torch.nn.functional as F
+    from oracle.transformer_tts import tts_loss
+    g = torch.Generator().manual_seed(5)
+    B, T = 3, 17
+    mels = torch.randn(B, T, 80, generator=g)
+    before, after, stop = torch.randn(B, T, 80, generator=g), torch.randn(B, T, 80, generator=g), torch.randn(B, T, generator=g)
+    lens = torch.full((B,), T, dtype=torch.int32)
+    target = torch.zeros(B, T); target[:, -1] = 1.0
+    want = F.mse_loss(before, mels) + F.mse_loss(after, mels) + \
+        F.binary_cross_entropy_with_logits(stop, target, pos_weight=torch.tensor(5.0))
+    got = tts_loss(before, after, stop, mels, lens)
+    assert torch.allclose(got, want, atol=1e-6, rtol=1e-6)
+    # padded frames contribute nothing
+    lens2 = torch.tensor([T, T - 5, 3], dtype=torch.int32)
+    m = (torch.arange(T)[None, :] < lens2[:, None]).float()
+    noisy = tts_loss(before + (1 - m)[..., None] * 100.0, after, stop + (1 - m) * 50.0, mels, lens2)
+    clean = tts_loss(before, after, stop, mels, lens2)
+    assert torch.allclose(noisy, clean, atol=1e-6)

@@ -206,3 +206,30 @@ def test_peer_adam_kernel_world1_equals_plain_adam(oracle_model):
     la, lb = float(ta.forward_backward(*inputs, seed=5)), float(tb.forward_backward(*inputs, seed=5))
     # (1e-7 parameter differences flip the bf16 rounding of a few weights in the operand copies: allow 2e-3)
     assert abs(la - lb) <= 2e-3 * abs(la), (la, lb)
+
+
+def test_train_step_vs_committed_golden(oracle_model):
+    """The same training step against the committed fixture (tests/golden/train_small.npz, made by make_golden.py from the
+    oracle): loss, train-mode outputs, gradient norms of every tensor and the small gradients element-wise."""
+    import os
+    import numpy as np
+    from transformer_tacotron2_b200.training import Trainer
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_small.npz"))
+    tr = Trainer(make_b200_model(oracle_model))
+    loss = tr.forward_backward(torch.from_numpy(g["phonemes"]), torch.from_numpy(g["phoneme_lens"]), torch.from_numpy(g["mels"]),
+                               torch.from_numpy(g["mel_lens"]), seed=int(g["seed"]))
+    assert abs(float(loss) - float(g["loss"])) < TOL_LOSS * float(g["loss"])
+    assert rel_l2(tr.outputs()[1], torch.from_numpy(g["mel_after"])) < TOL_OUT
+    grads = tr.grads()
+    total = float(np.sqrt((g["grad_norms"] ** 2).sum()))
+    for name, want in zip(g["names"], g["grad_norms"]):
+        got = float(grads[str(name)].norm())
+        if want > 1e-3 * total:
+            tol = TOL_GRAD_SCALAR if grads[str(name)].numel() == 1 else 0.1       # alphas: cancellation, see above
+            assert abs(got - want) < tol * want, (str(name), got, float(want))
+    for key in g.files:
+        if key.startswith("grad/"):
+            want = torch.from_numpy(g[key])
+            if float(want.norm()) > 1e-3 * total and want.numel() > 1:
+                assert rel_l2(grads[key[5:]], want) < TOL_GRAD, key
+    assert torch.allclose(tr.buffers()["postnet.convs.0.bn.running_mean"], torch.from_numpy(g["bn0_running_mean"]), atol=2e-2, rtol=2e-2)

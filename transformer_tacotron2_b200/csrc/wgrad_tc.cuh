@@ -27,20 +27,23 @@ struct WgradParams {
 
 struct WgradTcParams {
     alignas(64) CUtensorMap tm_dy, tm_x;     // bf16 {C, T, nb}, box {64, 64, 1}, SWIZZLE_128B
+    alignas(64) CUtensorMap tm_dw;           // fp32 {Cin, Cout}, box {32, 32}, SWIZZLE_128B: TMA reduce-add of the partial tiles (taps == 1)
+    int tma_red;
     WgradParams g;
     int tiles_m, tiles_n, n_tiles;           // output tiles: Cout/128 x Cin/128 x taps
     int kb_per_utt, n_kb, splits, kb_per_split, n_items;
 };
 
 constexpr int WG_STAGES = 4, WG_STAGE_BYTES = 32768, WG_THREADS = 192;
-constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 2048 + 256;    // ring + ones tile + barriers
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 2048 + 4 * 4096 + 256;    // ring + ones tile + output staging + barriers
 constexpr uint32_t WG_IDESC_ONES = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr uint32_t WG_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
     extern __shared__ __align__(1024) unsigned char wg_smem[];
     unsigned char* ones = wg_smem + WG_STAGES * WG_STAGE_BYTES;         // [16 tokens][64 features] of bf16 1.0
-    uint64_t* full = reinterpret_cast<uint64_t*>(ones + 2048);
+    unsigned char* ostage = ones + 2048;                                // [4 epilogue warps][32 rows x 128 B], 128B-swizzled
+    uint64_t* full = reinterpret_cast<uint64_t*>(ostage + 4 * 4096);
     uint64_t* empty = full + WG_STAGES;
     uint64_t* tmem_full = empty + WG_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -152,7 +155,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                     if (n < g.Cout) {
                         const int kcol = nt * 128 + c0;
                         float* o = g.dW + (size_t)n * ldo;
-                        if (g.taps == 1 && kcol + 32 <= g.Cin && (ldo & 3) == 0) {
+                        if (p.tma_red) {
+                            // handled below by the whole warp (rows past Cout / columns past Cin are clipped by the tensor map)
+                        } else if (g.taps == 1 && kcol + 32 <= g.Cin && (ldo & 3) == 0) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 4)
                                 fb_red4(o + kcol + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
@@ -162,6 +167,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                                 if (kcol + i < g.Cin) atomicAdd(o + (size_t)(kcol + i) * g.taps + tap, __uint_as_float(v[i]));
                         }
                     }
+                    if (p.tma_red && nt * 128 + c0 < g.Cin) {
+                        // one TMA reduce-add per 32 x 32 chunk instead of 32 per-row red instructions (32 request lines each)
+                        unsigned char* st = ostage + (warp - 2) * 4096;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<uint4*>(st + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                         ::"l"(&p.tm_dw), "r"(nt * 128 + c0), "r"(mt * 128 + lg * 32), "r"(tc_smem_u32(st)) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -169,6 +190,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             if (lane == 0 && nonempty) ft_arrive(&tmem_empty[acc]);
         }
     }
+    if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -198,6 +220,16 @@ inline cudaError_t launch_wgrad_tc(const WgradParams& g, cudaStream_t stream) {
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
     if (!make(&p.tm_dy, g.dY, g.Cout, g.ldy) || !make(&p.tm_x, g.X, g.Cin, g.ldx)) return cudaErrorInvalidValue;
+    p.tma_red = 0;
+    if (g.taps == 1 && (g.Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(g.dW) & 15) == 0) {
+        const cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Cout};
+        const cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 4};
+        const cuuint32_t box[2] = {32, 32};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&p.tm_dw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g.dW, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            p.tma_red = 1;
+    }
     p.tiles_m = (g.Cout + 127) / 128; p.tiles_n = (g.Cin + 127) / 128;
     p.n_tiles = p.tiles_m * p.tiles_n * g.taps;
     p.kb_per_utt = (g.T + 63) / 64; p.n_kb = p.kb_per_utt * g.nb;

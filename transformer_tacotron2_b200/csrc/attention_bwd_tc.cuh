@@ -86,6 +86,14 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
         for (int s = 0; s < 2; ++s) { tc_mbar_init(&s_full[s], 1); tc_mbar_init(&s_empty[s], FB_CWARPS); }
         tc_mbar_init(dp_full, 1); tc_mbar_init(dpq_free, FB_CWARPS); tc_mbar_init(ds_full, FB_CWARPS); tc_mbar_init(mma3_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (ni > 0) {                                    // producer thread: K / V and the first Q / dO tile go out under the TMEM allocation
+            tc_mbar_expect_tx(kv_full, 2 * FB_TILE);
+            ft_tma_4d(sK, &p.tm_k, 0, k0, h, b, kv_full);
+            ft_tma_4d(sV, &p.tm_v, 0, k0, h, b, kv_full);
+            tc_mbar_expect_tx(&qd_full[0], 2 * FB_TILE);
+            ft_tma_4d(sQ, &p.tm_q, 0, i0 * 128, h, b, &qd_full[0]);
+            ft_tma_4d(sdO, &p.tm_do, 0, i0 * 128, h, b, &qd_full[0]);
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(512) : "memory");
@@ -97,11 +105,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) flash_attn_bwd_tc_kernel(const 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0 && ni > 0) {                       // ---------------- TMA producer
-            tc_mbar_expect_tx(kv_full, 2 * FB_TILE);
-            ft_tma_4d(sK, &p.tm_k, 0, k0, h, b, kv_full);
-            ft_tma_4d(sV, &p.tm_v, 0, k0, h, b, kv_full);
-            for (int it = 0; it < ni; ++it) {
+        if (lane == 0 && ni > 0) {                       // ---------------- TMA producer (K, V and tile 0 were issued in the prologue)
+            for (int it = 1; it < ni; ++it) {
                 const int s = it % FB_QSTAGES; const uint32_t use = it / FB_QSTAGES;
                 if (use > 0) tc_mbar_wait(&qd_empty[s], (use & 1) ^ 1);
                 tc_mbar_expect_tx(&qd_full[s], 2 * FB_TILE);

@@ -150,6 +150,16 @@ __global__ void __launch_bounds__(FT_THREADS, 2) flash_attn_tc_kernel(const __gr
         for (int i = 0; i < 2; ++i) { tc_mbar_init(&k_full[i], 1); tc_mbar_init(&k_empty[i], 1); tc_mbar_init(&v_full[i], 1); tc_mbar_init(&v_empty[i], 1); }
         tc_mbar_init(s_full, 1); tc_mbar_init(s_empty, 4); tc_mbar_init(p_full, 4); tc_mbar_init(t_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // this thread is also the TMA producer: the first loads go out now, underneath the TMEM allocation and the block-wide
+        // barrier (at L = 800 a CTA lives for ~4 tiles, so its prologue is a third of its life)
+        if (nt > 0) {
+            tc_mbar_expect_tx(q_full, FT_TILE_BYTES);
+            ft_tma_4d(sQ, &p.tm_q, 0, q0, h, b, q_full);
+            tc_mbar_expect_tx(&k_full[0], FT_TILE_BYTES);
+            ft_tma_4d(sK, &p.tm_k, 0, 0, h, b, &k_full[0]);
+            tc_mbar_expect_tx(&v_full[0], FT_TILE_BYTES);
+            ft_tma_4d(sV, &p.tm_v, 0, 0, h, b, &v_full[0]);
+        }
     }
     if (warp == 1) {                                     // TMEM: S cols 0..127 (fp32), O 128..191 (fp32), P 192..255 (bf16 pairs)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(FT_TMEM_COLS) : "memory");
@@ -161,10 +171,8 @@ __global__ void __launch_bounds__(FT_THREADS, 2) flash_attn_tc_kernel(const __gr
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0 && nt > 0) {                       // ---------------- TMA producer
-            tc_mbar_expect_tx(q_full, FT_TILE_BYTES);
-            ft_tma_4d(sQ, &p.tm_q, 0, q0, h, b, q_full);
-            for (int j = 0; j < nt; ++j) {
+        if (lane == 0 && nt > 0) {                       // ---------------- TMA producer (Q and tile 0 were issued in the prologue)
+            for (int j = 1; j < nt; ++j) {
                 const int s = j & 1; const uint32_t use = j >> 1;
                 if (use > 0) tc_mbar_wait(&k_empty[s], (use & 1) ^ 1);
                 tc_mbar_expect_tx(&k_full[s], FT_TILE_BYTES);

@@ -238,12 +238,16 @@ class TransformerTTS(nn.Module):
     # ------------------------------------------------------------------ greedy AR
     @torch.no_grad()
     def inference(self, phonemes, phoneme_lens, max_len: int = 800, seed: int = 0, utt_ids=None, utt_offset: int = 0,
-                  return_before: bool = False):
+                  return_before: bool = False, clone_outputs: bool = True):
         """-> mel_after [B,Tout,80], mel_lens [B] i32, stop_logits [B,Tout].
 
         CPU tensors in -> the whole call runs through tts_infer_host (H2D, encoder, decode loop,
         postnet, D2H) and CPU tensors come back.  CUDA tensors in -> device-resident pipeline
-        (tts_encode / tts_decode_* ), CUDA tensors out."""
+        (tts_encode / tts_decode_* ), CUDA tensors out.
+
+        Host path: results are read back into pinned staging buffers the module keeps per (B, max_len).  With
+        clone_outputs=True (default) private copies are returned; clone_outputs=False returns views of the staging buffers,
+        valid until the next host-path call with the same shape (serving loops that consume the mel right away)."""
         lib = self._ensure_handle()
         self.sync_weights()
         B, S = phonemes.shape
@@ -252,14 +256,19 @@ class TransformerTTS(nn.Module):
         if not phonemes.is_cuda and not return_before:
             ph = phonemes.to(torch.int64).contiguous()
             pl = phoneme_lens.to(torch.int32).contiguous()
-            ma = torch.empty(B, max_len, 80).pin_memory(); st = torch.empty(B, max_len).pin_memory()
-            ml = torch.empty(B, dtype=torch.int32).pin_memory()
+            key = (B, int(max_len))
+            if getattr(self, "_host_out_key", None) != key:
+                self._host_out = (torch.empty(B, max_len, 80).pin_memory(), torch.empty(B, max_len).pin_memory(),
+                                  torch.empty(B, dtype=torch.int32).pin_memory())
+                self._host_out_key = key
+            ma, st, ml = self._host_out
             tout = C.c_int(0)
             rc = lib.tts_infer_host(self._handle, ws.data_ptr(), ph.data_ptr(), pl.data_ptr(), B, S, int(max_len), int(seed), u0,
                                     ma.data_ptr(), ml.data_ptr(), st.data_ptr(), C.byref(tout), self._stream())
             self._check(rc, "tts_infer_host")
             T = tout.value
-            return (ma.view(-1)[: B * T * 80].view(B, T, 80).clone(), ml.clone(), st.view(-1)[: B * T].view(B, T).clone())
+            out = (ma.view(-1)[: B * T * 80].view(B, T, 80), ml, st.view(-1)[: B * T].view(B, T))
+            return tuple(t.clone() for t in out) if clone_outputs else out
         dev = self.device
         ph = phonemes.to(dev, torch.int64).contiguous()
         pl = phoneme_lens.to(dev, torch.int32).contiguous()

@@ -19,7 +19,17 @@ TOL_LOSS = 5e-3       # relative error of the scalar loss
 # Measured: 0.4 % (heads) .. 3 % (mid network) .. 7.4 % (encoder prenet convs), whole gradient 1.7-3.6 %.
 TOL_GRAD = 1.2e-1     # rel-L2 of every parameter gradient with a non-negligible norm
 TOL_GRAD_ALL = 5e-2   # rel-L2 of the whole flat gradient
-TOL_GRAD_SCALAR = 4e-1  # enc_alpha / dec_alpha: sums of sign-alternating products (cancellation) on the smallest case
+TOL_GRAD_SCALAR = 1e-1  # enc_alpha / dec_alpha on cases with >= 1000 decoder frames (measured 0.9 % / 2.6 %)
+
+
+def _check_scalar_grad(name, got, want, n_frames):
+    """The alphas' gradients are sums of sign-alternating products over (frames x 512): on tiny cases cancellation turns the
+    ~3 % element error into tens of percent of the (small) sum -- and the fp32 atomics make that vary from run to run -- so
+    there only sign and order of magnitude are checked; the large cases pin the value."""
+    if n_frames >= 1000:
+        assert abs(got - want) < TOL_GRAD_SCALAR * abs(want), (name, got, want)
+    else:
+        assert got * want > 0 and 0.3 < got / want < 3.0, (name, got, want)
 
 
 def _oracle_step(oracle_model, inputs, seed):
@@ -59,7 +69,7 @@ def test_train_step_gradients(oracle_model, B, S, T, ragged):
         num += float((got - want).norm() ** 2)
         if want.norm() > 1e-3 * total_ref:                       # tensors that matter; tiny ones are covered by the global check
             if want.numel() == 1:
-                assert rel_l2(got, want) < TOL_GRAD_SCALAR, (k, float(got), float(want))
+                _check_scalar_grad(k, float(got), float(want), B * T)
             else:
                 worst.append((rel_l2(got, want), k))
     worst.sort(reverse=True)
@@ -225,8 +235,10 @@ def test_train_step_vs_committed_golden(oracle_model):
     for name, want in zip(g["names"], g["grad_norms"]):
         got = float(grads[str(name)].norm())
         if want > 1e-3 * total:
-            tol = TOL_GRAD_SCALAR if grads[str(name)].numel() == 1 else 0.1       # alphas: cancellation, see above
-            assert abs(got - want) < tol * want, (str(name), got, float(want))
+            if grads[str(name)].numel() == 1:                                   # alphas (norm = |value|): see _check_scalar_grad
+                assert 0.3 < got / want < 3.0, (str(name), got, float(want))
+            else:
+                assert abs(got - want) < 0.1 * want, (str(name), got, float(want))
     for key in g.files:
         if key.startswith("grad/"):
             want = torch.from_numpy(g[key])

@@ -308,11 +308,12 @@ __global__ void attn_dsum_kernel(const bf16* O, const bf16* dO, long o_bs, long 
 }
 
 inline cudaError_t launch_flash_attn_bwd_tc(const AttnBwdParams& a, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(flash_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES);
+    static PerDevice pd;
+    {
+        const cudaError_t e = per_device_once(pd, nullptr, [] {
+            return cudaFuncSetAttribute(flash_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES);
+        });
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     TcEncodeFn enc = tc_encode_fn();
     if (!enc) return cudaErrorInvalidValue;

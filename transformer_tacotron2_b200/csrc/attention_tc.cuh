@@ -333,11 +333,12 @@ __global__ void __launch_bounds__(FT_THREADS, 2) flash_attn_tc_kernel(const __gr
 }
 
 inline cudaError_t launch_flash_attn_tc(const AttnParams& a, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(flash_attn_tc_kernel<FT_POLY_EVERY>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES);
+    static PerDevice pd;
+    {
+        const cudaError_t e = per_device_once(pd, nullptr, [] {
+            return cudaFuncSetAttribute(flash_attn_tc_kernel<FT_POLY_EVERY>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES);
+        });
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     TcEncodeFn enc = tc_encode_fn();
     if (!enc) return cudaErrorInvalidValue;

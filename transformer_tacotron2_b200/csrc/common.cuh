@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <math.h>
+#include <mutex>
 
 typedef __nv_bfloat16 bf16;
 
@@ -14,6 +15,40 @@ namespace tts {
 
 // Kernel launches issued by this library since load (bench.py reports it as gpu_launches).
 inline unsigned long long& launch_counter() { static unsigned long long n = 0; return n; }
+
+// One-time per-DEVICE launcher state (cudaFuncSetAttribute and the SM count are per device; a process may hold handles on
+// several GPUs).  `setup` runs once for the calling thread's current device; *num_sms receives that device's SM count.
+struct PerDevice {
+    std::mutex mu;
+    bool done[64] = {};
+    int sms[64] = {};
+};
+template <class Fn>
+inline cudaError_t per_device_once(PerDevice& s, int* num_sms, Fn setup) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(s.mu);
+    if (!s.done[dev]) {
+        if ((e = setup()) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&s.sms[dev], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        s.done[dev] = true;
+    }
+    if (num_sms) *num_sms = s.sms[dev];
+    return cudaSuccess;
+}
+// Makes `dev` current for the lifetime of the guard and restores the caller's device afterwards (the C ABI must not
+// change the current device under PyTorch's feet).
+struct DeviceGuard {
+    int prev = -1, target;
+    cudaError_t err;
+    explicit DeviceGuard(int dev) : target(dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != target) cudaSetDevice(prev); }
+};
 
 constexpr int kDModel = 512;     // the base model is the only model on this path
 constexpr int kHeads = 8;
@@ -46,33 +81,6 @@ TTS_D float warp_max(float v) {
     return v;
 }
 
-// Loads of data that other CTAs of the SAME launch may have written (after a grid barrier):
-// L2-coherent, never served from a stale L1 line.
-TTS_D uint4 ld_cg_u4(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-TTS_D float4 ld_cg_f4(const void* p) {
-    float4 r;
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-TTS_D float2 ld_cg_f2(const void* p) {
-    float2 r;
-    asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-}
-TTS_D float ld_cg_f(const void* p) {
-    float r;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
-}
-TTS_D int ld_cg_i(const void* p) {
-    int r;
-    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
 // L2 eviction policies (createpolicy): KV-cache rows are streamed once per step -> evict_first, so
 // they do not push the weights (re-read every step, 44.7 MB) out of the 126 MB L2 -> evict_last.
 TTS_D uint64_t l2_policy_evict_first() {
@@ -85,21 +93,6 @@ TTS_D uint64_t l2_policy_evict_last() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-// Streaming KV-cache rows: L2-coherent (never allocated in L1), with an L2 cache-hint policy.
-TTS_D uint4 ld_stream_u4(const void* p, uint64_t pol) {
-    uint4 r;
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
-    return r;
-}
-// Read-only for the whole launch (weights): non-coherent path.
-TTS_D uint4 ld_weight_u4(const void* p, uint64_t pol) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
-    return r;
-}
-
 // ---------------------------------------------------------------- warp-level bf16 MMA (m16n8k16)
 TTS_D void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

@@ -73,7 +73,7 @@ struct ClusterParams {
     alignas(64) CUtensorMap tm_cross;
     int B, Tmax, S, G, ngroups;                  // G utterances per cluster (<= 8)
     int Tpad, Spad;                              // cache row capacities, multiples of 16
-    uint64_t seed; int utt_offset; float dec_alpha; const float* pe;
+    uint64_t seed; int utt_offset; float dec_alpha; float ln_eps; const float* pe;
     const unsigned char* wpack;                  // [8][CLW_RANK_BYTES]
     const float *b_fc1, *b_fc2, *b_proj, *b_head;
     ClusterLayerParams layer[6];
@@ -98,17 +98,10 @@ TTS_D uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
     return r;
 }
-TTS_D void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c2, uint32_t d) {
-    asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c2), "r"(d) : "memory");
-}
-TTS_D void red_cluster_add_u32(uint32_t addr, uint32_t v) { asm volatile("red.shared::cluster.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 TTS_D void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
 TTS_D void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 TTS_D void mbar_arrive_n(uint64_t* bar, uint32_t n) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
-}
-TTS_D void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 TTS_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -116,12 +109,6 @@ TTS_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 TTS_D bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-TTS_D bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
@@ -138,11 +125,10 @@ TTS_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, u
 // ---------------------------------------------------------------- per-CTA context (consumer side)
 struct ClCtx {
     unsigned char* smem;
-    uint64_t *full, *empty, *csync, *gsync;   // ring full/empty, classic cluster barrier, data-carrying gather barriers [2]
+    uint64_t *full, *empty, *gsync;           // ring full/empty, data-carrying gather barriers [2]
     int rank, tid, warp, lane;
     int b0, G;                           // group base utterance, rows in this group
     uint32_t consumed;                   // chunks consumed (uniform over the consumer warps)
-    uint32_t sync_phase;                 // cluster barrier phase counter
     uint32_t gphase;                     // gather phase counter (40 per decoder step)
 };
 
@@ -185,6 +171,10 @@ TTS_D uint32_t seg_weight_bytes(int seg) {          // bytes per chunk of a weig
 // consumers raise flags[1].  The control flow is warp-uniform.
 TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* full, uint64_t* empty, volatile int* flags,
                        int rank, int b0, int G, int t0, int t_end, int lane) {
+    // ONE lane runs the whole loop alone (the other 31 go straight to the group-end barrier): a warp-wide loop with
+    // lane-0-predicated copies and a __syncwarp per chunk costs ~0.35 us per chunk, a lone lane ~0.16 us
+    // (scripts/ubench/ring_bisect2.cu, profiles/r02_ring_ubench.md) -- the difference between 90 and 200 GB/s per SM.
+    if (lane != 0) return;
     const uint64_t pol_w = l2_policy_evict_last(), pol_kv = l2_policy_evict_first();
     uint32_t issued = 0;
     const unsigned char* wbase = p.wpack + (size_t)rank * CLW_RANK_BYTES;
@@ -198,44 +188,37 @@ TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* fu
                 const int stage = issued % CL_STAGES;
                 const uint32_t use = issued / CL_STAGES;
                 if (use > 0) {
-                    for (;;) {                           // all lanes poll (see cl_acquire); the decision is made warp-uniform
-                        const int ok = mbar_try_wait(&empty[stage], (use & 1) ^ 1) ? 1 : 0;
-                        if (__any_sync(0xffffffffu, ok)) break;
-                        if (__any_sync(0xffffffffu, flags[1])) { stopped = true; break; }
+                    while (!mbar_try_wait(&empty[stage], (use & 1) ^ 1)) {
+                        if (flags[1]) { stopped = true; break; }
                     }
                     if (stopped) break;
                 }
                 unsigned char* dst = smem + SM_RING + stage * CL_STAGE_BYTES;
                 if (sub == 1 || sub == 4) {                      // 16 K rows + one V block of every pair (b0.., head rank): 2 TMA boxes
-                    if (lane == 0) {
-                        const int l = (seg - 3) >> 3;
-                        const CUtensorMap* tm = sub == 1 ? &p.tm_self : &p.tm_cross;
-                        mbar_expect_tx(&full[stage], 2u * (uint32_t)p.G * 2048u);
-                        tma_g2s_4d(dst, tm, 0, i * CL_KV_ROWS, rank, (l * 2) * p.B + b0, &full[stage], pol_kv);
-                        tma_g2s_4d(dst + 16384, tm, 0, i * CL_KV_ROWS, rank, (l * 2 + 1) * p.B + b0, &full[stage], pol_kv);
-                    }
-                } else if (lane == 0) {
+                    const int l = (seg - 3) >> 3;
+                    const CUtensorMap* tm = sub == 1 ? &p.tm_self : &p.tm_cross;
+                    mbar_expect_tx(&full[stage], 2u * (uint32_t)p.G * 2048u);
+                    tma_g2s_4d(dst, tm, 0, i * CL_KV_ROWS, rank, (l * 2) * p.B + b0, &full[stage], pol_kv);
+                    tma_g2s_4d(dst + 16384, tm, 0, i * CL_KV_ROWS, rank, (l * 2 + 1) * p.B + b0, &full[stage], pol_kv);
+                } else {
                     const uint32_t bytes = seg_weight_bytes(seg);
                     mbar_expect_tx(&full[stage], bytes);
                     bulk_g2s(dst, wbase + woff, bytes, &full[stage], pol_w);
+                    woff += bytes;
                 }
-                if (!(sub == 1 || sub == 4)) woff += seg_weight_bytes(seg);
                 {
                     const int nskip = CL_WARPS - seg_readers(seg, G);
-                    if (lane == 0 && nskip > 0) mbar_arrive_n(&empty[stage], (uint32_t)nskip);
+                    if (nskip > 0) mbar_arrive_n(&empty[stage], (uint32_t)nskip);
                 }
                 ++issued;
             }
         }
     }
     // wait until the consumers are done with the group, then drain copies that were issued but never consumed
-    if (lane == 0) {
-        while (!flags[1]) {}
-        __threadfence_block();
-        const uint32_t final_consumed = (uint32_t)flags[2];
-        for (uint32_t i = final_consumed; i < issued; ++i) mbar_wait(&full[i % CL_STAGES], (i / CL_STAGES) & 1);
-    }
-    __syncwarp();
+    while (!flags[1]) {}
+    __threadfence_block();
+    const uint32_t final_consumed = (uint32_t)flags[2];
+    for (uint32_t i = final_consumed; i < issued; ++i) mbar_wait(&full[i % CL_STAGES], (i / CL_STAGES) & 1);
 }
 
 TTS_D unsigned char* cl_acquire(ClCtx& c) {
@@ -249,13 +232,6 @@ TTS_D void cl_release(ClCtx& c) {
     __syncwarp();
     if (c.lane == 0) mbar_arrive(&c.empty[c.consumed % CL_STAGES]);
     ++c.consumed;
-}
-// cluster-wide barrier of the consumer warps: my DSMEM pushes are visible to every peer afterwards
-TTS_D void cl_sync(ClCtx& c) {
-    consumer_bar();
-    if (c.tid < CL_SIZE) mbar_arrive_remote(map_to_rank(smem_u32(c.csync), (uint32_t)c.tid));
-    while (!mbar_try_wait_cluster(c.csync, c.sync_phase & 1)) {}
-    ++c.sync_phase;
 }
 
 // ---------------------------------------------------------------- GEMM over ring chunks
@@ -400,7 +376,7 @@ TTS_D void ln_prefetch(const ClCtx& c, const float* g, const float* b) {
     }
     cp_async_commit();
 }
-TTS_D void cl_layernorm(ClCtx& c) {
+TTS_D void cl_layernorm(ClCtx& c, float ln_eps) {
     cp_async_wait<0>();
     consumer_bar();
     if (c.warp < c.G) {
@@ -421,7 +397,7 @@ TTS_D void cl_layernorm(ClCtx& c) {
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; ss += d * d; }
-        const float rstd = rsqrtf(warp_sum(ss) * (1.f / 512.f) + 1e-5f);
+        const float rstd = rsqrtf(warp_sum(ss) * (1.f / 512.f) + ln_eps);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int col = i * 128 + c.lane * 4;
@@ -576,15 +552,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
     c.smem = cl_smem;
     c.full = reinterpret_cast<uint64_t*>(cl_smem + SM_MISC);
     c.empty = c.full + CL_STAGES;
-    c.csync = c.empty + CL_STAGES;
-    c.gsync = c.csync + 1;
+    c.gsync = c.empty + CL_STAGES;
     // flags[0] finished utterances of the group (rank 5 counts), [1] consumers done (producer stop), [2] final consumed count
     // hrec: one 16-byte record per rank, pushed in the head phase (rank 5: finished count)
     volatile int* flags = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 128);
     volatile int* hrec = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 128 + 32);     // [8 ranks][4]
     c.rank = (int)cluster_ctarank();
     c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
-    c.sync_phase = 0;
     const int cid = (int)cluster_id_x(), ncl = (int)cluster_nid_x();
     const bool is_producer = c.warp == CL_WARPS;
 
@@ -607,12 +581,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
             p.ts[(size_t)t * 64 + idx] = now;
         }
     };
-
-    if (c.tid == 0) {
-        mbar_init(c.csync, CL_SIZE);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    hw_cluster_sync();                                   // csync barriers of all peers exist before any remote arrive
 
     for (int grp = cid; grp < p.ngroups; grp += ncl) {
         c.b0 = grp * p.G; c.G = min(p.G, p.B - c.b0);
@@ -640,12 +608,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
         const bool skip = flags[0] >= c.G;               // every utterance of the group already finished
         __syncthreads();
 
-        if (is_producer) {
-            if (!skip) cl_producer(p, cl_smem, c.full, c.empty, flags, c.rank, c.b0, c.G, t0, t0 + n_steps, c.lane);
-        } else if (skip) {
-            cl_sync(c); cl_sync(c);
+        // Group boundaries use the hardware cluster barrier (all 544 threads of all 8 CTAs): every peer's buffers and
+        // mbarriers are initialised before any DSMEM push reaches them, and nobody re-initialises them while a peer is
+        // still inside the group.  (`skip` is uniform over the cluster: every CTA reads the same finished[] flags.)
+        hw_cluster_sync();
+        if (skip) {
+        } else if (is_producer) {
+            cl_producer(p, cl_smem, c.full, c.empty, flags, c.rank, c.b0, c.G, t0, t0 + n_steps, c.lane);
+            __syncwarp();                                // lanes 1..31 park here: the cluster barrier below is .aligned
         } else {
-            cl_sync(c);                                  // peers' buffers are initialised before any DSMEM push
             for (int t = t0; t < t0 + n_steps; ++t) {
                 // ================= decoder prenet (dropout always on, P7) =================
                 cl_gemm(c, 1, 2, 2, false, fbuf, LDX128,
@@ -711,7 +682,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     ln_prefetch(c, W.ln1g, W.ln1b);
                     push_f32_all(c, stg, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
                     gather_wait(c);
-                    cl_layernorm(c);
+                    cl_layernorm(c, p.ln_eps);
                     stamp(t, 5 + 8 * l);
                     // ---- cross-attention query of head `rank` (local)
                     cl_gemm(c, 2, 4, 4, false, xa, LDX512,
@@ -730,7 +701,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     ln_prefetch(c, W.ln2g, W.ln2b);
                     push_f32_all(c, stg, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
                     gather_wait(c);
-                    cl_layernorm(c);
+                    cl_layernorm(c, p.ln_eps);
                     stamp(t, 8 + 8 * l);
                     // ---- FFN: hidden slice [256 rank, +256) stays local (bf16); FFN2 is split along K
                     cl_gemm(c, 8, 16, 1, false, xa, LDX512,
@@ -766,7 +737,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         push_f32_all(c, st2, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
                     }
                     gather_wait(c);
-                    cl_layernorm(c);
+                    cl_layernorm(c, p.ln_eps);
                     stamp(t, 10 + 8 * l);
                 }
                 // ================= [mel | stop] heads: ranks 0..5 own 16 of the 81(+15) columns =================
@@ -796,14 +767,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                 stamp(t, 51);
                 if (hrec[5 * 4] >= c.G) break;                               // every utterance of the group has fired
             }
-            // ---- tell the producer we are done; peers finish the group before anyone re-initialises buffers
+            // ---- tell the producer we are done (it drains the copies that were issued but never consumed)
             consumer_bar();
             if (c.tid == 0) { flags[2] = (int)c.consumed; __threadfence_block(); flags[1] = 1; }
-            cl_sync(c);
         }
-        __syncthreads();                                 // producer has drained the ring
+        hw_cluster_sync();                               // peers have finished the group; no CTA exits (or re-initialises) while a
+                                                         // peer may still touch its shared memory
     }
-    hw_cluster_sync();                                   // no CTA exits while a peer may still touch its shared memory
 }
 
 }  // namespace tts

@@ -327,14 +327,15 @@ inline TcEncodeFn tc_encode_fn() {
 // Same contract as launch_gemm (gemm_epilogue.cuh): g.A / g.W are bf16 row-major, lda / ldw in elements (multiples of 8),
 // W has taps * Nw rows (Nw = N rounded up to 128).  Returns cudaErrorInvalidValue for shapes it cannot describe.
 inline cudaError_t launch_gemm_tc(const GemmParams& g, cudaStream_t stream) {
-    static bool attr_set = false;
-    static int num_sms = 0;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(256));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(128));
+    static PerDevice pd;
+    int num_sms = 0;
+    {
+        const cudaError_t e = per_device_once(pd, &num_sms, [] {
+            cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(256));
+            if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(128));
+            return e2;
+        });
         if (e != cudaSuccess) return e;
-        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        attr_set = true;
     }
     TcEncodeFn enc = tc_encode_fn();
     if (!enc || (g.lda & 7) || (g.ldw & 7) || (g.M % g.T) != 0) return cudaErrorInvalidValue;

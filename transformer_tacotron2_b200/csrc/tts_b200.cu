@@ -69,6 +69,8 @@ struct TtsHandle {
         }                                                                                            \
     } while (0)
 #define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
+// makes the handle's device current for the rest of the entry point and restores the caller's device on return
+#define DEV_GUARD(h) DeviceGuard dev_guard_((h)->device); CK(dev_guard_.err)
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 static inline uint16_t f2bf(float f) {                                // round-to-nearest-even, as __float2bfloat16_rn
@@ -117,7 +119,8 @@ extern "C" int tts_create(const TtsConfig* cfg, int device, TtsHandle** out) {
     if (!cfg || !out || cfg->struct_size != sizeof(TtsConfig)) return TTS_E_ARG;
     if (cfg->d_model != 512 || cfg->n_heads != 8 || cfg->d_ff != 2048 || cfg->n_mels != 80 || cfg->d_prenet != 256 ||
         cfg->conv_kernel != 5 || cfg->n_enc_layers != 6 || cfg->n_dec_layers != 6 || cfg->enc_conv_layers != 3 ||
-        cfg->postnet_layers != 5 || cfg->postnet_channels != 512 || cfg->max_pos < 1 || cfg->n_vocab < 1)
+        cfg->postnet_layers != 5 || cfg->postnet_channels != 512 || cfg->max_pos < 1 || cfg->n_vocab < 1 ||
+        !(cfg->ln_eps > 0.f) || !(cfg->bn_eps > 0.f))
         return TTS_E_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return TTS_E_DEVICE;
@@ -125,7 +128,8 @@ extern "C" int tts_create(const TtsConfig* cfg, int device, TtsHandle** out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return TTS_E_DEVICE;
     TtsHandle* h = new TtsHandle();
     h->cfg = *cfg; h->device = device; h->num_sms = prop.multiProcessorCount;
-    if (cudaSetDevice(device) != cudaSuccess) { delete h; return TTS_E_DEVICE; }
+    DeviceGuard dev_guard_(device);
+    if (dev_guard_.err != cudaSuccess) { delete h; return TTS_E_DEVICE; }
     if (cudaMallocHost(&h->h_status, 64) != cudaSuccess) { delete h; return TTS_E_DEVICE; }
     *out = h;
     return 0;
@@ -134,8 +138,9 @@ extern "C" int tts_create(const TtsConfig* cfg, int device, TtsHandle** out) {
 extern "C" int tts_train_end(TtsHandle* h);
 extern "C" int tts_destroy(TtsHandle* h) {
     if (!h) return TTS_E_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard_(h->device);
     if (h->arena) cudaFree(h->arena);
+    if (h->pe) cudaFree(h->pe);
     if (h->cl_wpack) cudaFree(h->cl_wpack);
     if (h->h_status) cudaFreeHost(h->h_status);
     tts_train_end(h);
@@ -223,7 +228,7 @@ std::vector<int> iota_rows(int lo, int n) { std::vector<int> r(n); for (int i = 
 
 extern "C" int tts_finalize_weights(TtsHandle* h) {
     if (!h) return TTS_E_ARG;
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     const TtsConfig& c = h->cfg;
     std::string missing;
     auto get = [&](const std::string& k, size_t numel) -> const float* {
@@ -332,14 +337,16 @@ extern "C" int tts_finalize_weights(TtsHandle* h) {
         bind(&h->head_w, pack_rowmajor(ar, w.data(), 81, D, 1, 128, D, nullptr));
         bind(&h->head_b, pack_f32(ar, b.data(), 81, 128));
     }
-    {   // P4 sinusoid table, fp32 rounded from float64 (same definition as oracle.sinusoid_table)
+    if (!h->pe) {   // P4 sinusoid table, fp32 rounded from float64 (same definition as oracle.sinusoid_table).  Its own allocation,
+                    // made once per handle: a captured training graph and a live decode session keep its address across re-finalisation
         std::vector<float> pe((size_t)c.max_pos * D);
         for (int pos = 0; pos < c.max_pos; ++pos)
             for (int i = 0; i < D; i += 2) {
                 const double ang = (double)pos / std::pow(10000.0, (double)i / D);
                 pe[(size_t)pos * D + i] = (float)std::sin(ang); pe[(size_t)pos * D + i + 1] = (float)std::cos(ang);
             }
-        bind(&h->pe, pack_f32(ar, pe.data(), pe.size()));
+        CK(cudaMalloc(&h->pe, pe.size() * 4));
+        CK(cudaMemcpy(h->pe, pe.data(), pe.size() * 4, cudaMemcpyHostToDevice));
     }
     // ---- per-rank weight streams of the cluster decode kernel (decode_cluster.cuh), in consumption order
     std::vector<unsigned char> clw((size_t)CL_SIZE * CLW_RANK_BYTES);
@@ -387,6 +394,7 @@ extern "C" int tts_finalize_weights(TtsHandle* h) {
     CK(cudaMemcpy(h->arena, ar.host.data(), ar.host.size(), cudaMemcpyHostToDevice));
     for (auto& f : fixes) *f.dst = h->arena + f.off;
     CK(cudaDeviceSynchronize());
+    h->dec_active = false;                                            // a decode session holds pointers into the old arena
     h->finalized = true;                                              // (the staged fp32 copies stay: tts_train_begin builds the master from them)
     return 0;
 }
@@ -497,7 +505,7 @@ extern "C" int tts_encode(TtsHandle* h, void* ws, const int64_t* phonemes, const
     if (!h || !ws || !phonemes || !phoneme_lens || B <= 0 || S <= 0 || T <= 0) return TTS_E_ARG;
     if (!h->finalized) FAIL(TTS_E_STATE, "weights not finalised");
     if (S > h->cfg.max_pos) FAIL(TTS_E_ARG, "S exceeds max_pos");
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     cudaStream_t st = (cudaStream_t)stream;
     const Ws L = Ws::make(B, S, T);
     // the decode phases read the key-padding lengths from the workspace copy
@@ -517,7 +525,7 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
     if (!h || !ws || B <= 0 || S <= 0 || max_len <= 0) return TTS_E_ARG;
     if (!h->finalized) FAIL(TTS_E_STATE, "weights not finalised");
     if (max_len > h->cfg.max_pos) FAIL(TTS_E_ARG, "max_len exceeds max_pos");
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     cudaStream_t st = (cudaStream_t)stream;
     const Ws L = Ws::make(B, S, max_len);
     h->dec_active = true; h->dec_B = B; h->dec_S = S; h->dec_T = max_len; h->dec_t = 0; h->dec_seed = seed; h->dec_utt0 = utt_offset;
@@ -571,7 +579,7 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
         if (make(&cp.tm_self, wsp<bf16>(ws, L.self_kv), L.Tpad) != CUDA_SUCCESS || make(&cp.tm_cross, wsp<bf16>(ws, L.cross_kv), L.Spad) != CUDA_SUCCESS)
             FAIL(TTS_E_ARG, "cuTensorMapEncodeTiled failed for the K/V caches");
     }
-    cp.seed = seed; cp.utt_offset = utt_offset; cp.dec_alpha = h->dec_alpha; cp.pe = h->pe;
+    cp.seed = seed; cp.utt_offset = utt_offset; cp.dec_alpha = h->dec_alpha; cp.ln_eps = h->cfg.ln_eps; cp.pe = h->pe;
     cp.wpack = h->cl_wpack; cp.b_fc1 = h->pre_b1; cp.b_fc2 = h->pre_b2; cp.b_proj = h->pre_bp; cp.b_head = h->head_b;
     for (int l = 0; l < 6; ++l) {
         auto& W = h->dec[l];
@@ -586,7 +594,7 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
 extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* stream) {
     if (!h || !ws || n_steps < 0) return TTS_E_ARG;
     if (!h->dec_active) FAIL(TTS_E_STATE, "tts_decode_begin not called");
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     cudaStream_t st = (cudaStream_t)stream;
     n_steps = std::min(n_steps, h->dec_T - h->dec_t);
     if (n_steps <= 0) return 0;
@@ -606,7 +614,7 @@ extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* strea
 extern "C" int tts_decode_status(TtsHandle* h, void* ws, int* t_done, int* n_finished, void* stream) {
     if (!h || !ws) return TTS_E_ARG;
     if (!h->dec_active) FAIL(TTS_E_STATE, "tts_decode_begin not called");
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemcpyAsync(h->h_status, h->cparams.n_finished, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -628,7 +636,7 @@ extern "C" int tts_decode_end(TtsHandle* h, void* ws, int T_out, float* mel_afte
     if (!h || !ws || !mel_after || T_out <= 0) return TTS_E_ARG;
     if (!h->dec_active) FAIL(TTS_E_STATE, "tts_decode_begin not called");
     if (T_out > h->dec_T) FAIL(TTS_E_ARG, "T_out exceeds max_len");
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     cudaStream_t st = (cudaStream_t)stream;
     const int B = h->dec_B;
     const Ws L = Ws::make(B, h->dec_S, h->dec_T);
@@ -652,8 +660,11 @@ extern "C" int tts_infer_host(TtsHandle* h, void* ws, const int64_t* phonemes, c
                               int max_len, uint64_t seed, int utt_offset, float* mel_after, int32_t* mel_lens,
                               float* stop_logits, int* T_out, void* stream) {
     if (!h || !ws || !phonemes || !phoneme_lens || !mel_after || !mel_lens || !stop_logits || !T_out) return TTS_E_ARG;
+    if (B <= 0 || S <= 0 || max_len <= 0) FAIL(TTS_E_ARG, "B, S and max_len must be positive");
     if (!h->finalized) FAIL(TTS_E_STATE, "weights not finalised");
-    CK(cudaSetDevice(h->device));
+    if (S > h->cfg.max_pos) FAIL(TTS_E_ARG, "S exceeds max_pos");              // checked before any copy or launch
+    if (max_len > h->cfg.max_pos) FAIL(TTS_E_ARG, "max_len exceeds max_pos");
+    DEV_GUARD(h);
     cudaStream_t st = (cudaStream_t)stream;
     const Ws L = Ws::make(B, S, max_len);
     CK(cudaMemcpyAsync(wsp<int64_t>(ws, L.ph), phonemes, (size_t)B * S * 8, cudaMemcpyHostToDevice, st));
@@ -685,7 +696,7 @@ extern "C" int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, cons
     if (B <= 0 || S <= 0 || T <= 0) return TTS_E_ARG;
     if (!h->finalized) FAIL(TTS_E_STATE, "weights not finalised");
     if (S > h->cfg.max_pos || T > h->cfg.max_pos) FAIL(TTS_E_ARG, "sequence exceeds max_pos");
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     cudaStream_t st = (cudaStream_t)stream;
     const Ws L = Ws::make(B, S, T);
     int r = run_encoder(h, ws, L, phonemes, phoneme_lens, B, S, false, st);
@@ -858,7 +869,7 @@ extern "C" int tts_k_philox_bits(uint64_t seed, int site, int T, int B, int C, i
 extern "C" int tts_train_begin(TtsHandle* h) {
     if (!h) return TTS_E_ARG;
     if (!h->finalized) FAIL(TTS_E_STATE, "weights not finalised");
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     train_free(h);
     int r = train_build(h);
     if (r) { train_free(h); return r; }
@@ -866,7 +877,7 @@ extern "C" int tts_train_begin(TtsHandle* h) {
     CK(cudaDeviceSynchronize());
     return 0;
 }
-extern "C" int tts_train_end(TtsHandle* h) { if (!h) return TTS_E_ARG; cudaSetDevice(h->device); return train_free(h); }
+extern "C" int tts_train_end(TtsHandle* h) { if (!h) return TTS_E_ARG; DeviceGuard dev_guard_(h->device); return train_free(h); }
 extern "C" size_t tts_train_workspace_bytes(TtsHandle* h, int B, int S, int T) {
     if (!h || B <= 0 || S <= 0 || T <= 0) return 0;
     return TrWs::make(nullptr, B, S, T).total;
@@ -877,7 +888,7 @@ extern "C" int tts_train_step(TtsHandle* h, void* ws, const int64_t* phonemes, c
     if (!h->train) FAIL(TTS_E_STATE, "tts_train_begin has not been called");
     if (S > h->cfg.max_pos || T > h->cfg.max_pos) FAIL(TTS_E_ARG, "sequence exceeds max_pos");
     if (p_residual < 0.0 || p_residual >= 1.0) FAIL(TTS_E_ARG, "p_residual out of range");
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     TrCtx c;
     TtsTrain* t = h->train;
     c.h = h; c.t = t; c.w = TrWs::make(reinterpret_cast<unsigned char*>(ws), B, S, T); c.st = (cudaStream_t)stream;
@@ -940,7 +951,7 @@ extern "C" int tts_train_grads(TtsHandle* h, float** grads_dev, int64_t* numel) 
 }
 extern "C" int tts_train_adam(TtsHandle* h, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
     if (!h || !h->train) return TTS_E_ARG;
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     TtsTrain* t = h->train;
     cudaStream_t st = (cudaStream_t)stream;
     ++t->step;
@@ -954,14 +965,14 @@ extern "C" int tts_train_adam(TtsHandle* h, float lr, float beta1, float beta2, 
 extern "C" int tts_train_ipc_handles(TtsHandle* h, void* handle_P_64, void* handle_G_64) {
     if (!h || !h->train || !handle_P_64 || !handle_G_64) return TTS_E_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_P_64), h->train->P));
     CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_G_64), h->train->G));
     return 0;
 }
 extern "C" int tts_train_set_peers(TtsHandle* h, int rank, int world, const void* handles_P, const void* handles_G) {
     if (!h || !h->train || world < 1 || world > 8 || rank < 0 || rank >= world || (world > 1 && (!handles_P || !handles_G))) return TTS_E_ARG;
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     TtsTrain* t = h->train;
     for (void*& q : t->ipc_opened) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
     t->rank = rank; t->world = world;
@@ -982,7 +993,7 @@ extern "C" int tts_train_set_peers(TtsHandle* h, int rank, int world, const void
 // rank's shard has been written everywhere after (then tts_train_repack refreshes the bf16 operand copies).
 extern "C" int tts_train_adam_peers(TtsHandle* h, float lr, float beta1, float beta2, float eps, void* stream) {
     if (!h || !h->train) return TTS_E_ARG;
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     TtsTrain* t = h->train;
     ++t->step;
     const float bc1 = 1.f - std::pow(beta1, (float)t->step), bc2 = 1.f - std::pow(beta2, (float)t->step);
@@ -999,7 +1010,7 @@ extern "C" int tts_train_adam_peers(TtsHandle* h, float lr, float beta1, float b
 }
 extern "C" int tts_train_repack(TtsHandle* h, void* stream) {
     if (!h || !h->train) return TTS_E_ARG;
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     return train_repack(h, (cudaStream_t)stream);
 }
 extern "C" int tts_train_num_tensors(TtsHandle* h) { return (h && h->train) ? (int)(h->train->params.size() + h->train->buffers.size()) : -1; }
@@ -1018,7 +1029,7 @@ extern "C" int tts_train_read(TtsHandle* h, int which, int64_t offset, int64_t n
     const float* src = which == 0 ? t->P : which == 1 ? t->G : which == 2 ? t->RS : nullptr;
     const size_t lim = which == 2 ? t->nrs : t->n;
     if (!src || (size_t)(offset + numel) > lim) return TTS_E_ARG;
-    CK(cudaSetDevice(h->device));
+    DEV_GUARD(h);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(host_out, src + offset, (size_t)numel * 4, cudaMemcpyDeviceToHost));
     return 0;

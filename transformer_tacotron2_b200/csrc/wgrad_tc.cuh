@@ -199,13 +199,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 }
 
 inline cudaError_t launch_wgrad_tc(const WgradParams& g, cudaStream_t stream) {
-    static bool attr_set = false;
-    static int num_sms = 0;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    static PerDevice pd;
+    int num_sms = 0;
+    {
+        const cudaError_t e = per_device_once(pd, &num_sms, [] {
+            return cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+        });
         if (e != cudaSuccess) return e;
-        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        attr_set = true;
     }
     TcEncodeFn enc = tc_encode_fn();
     if (!enc || (g.ldy & 7) || (g.ldx & 7)) return cudaErrorInvalidValue;

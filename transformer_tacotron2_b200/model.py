@@ -129,6 +129,9 @@ class TransformerTTS(nn.Module):
         self._lib = None
         self._handle = C.c_void_p()
         self._dirty = True
+        self._host_stale = False         # a Trainer has stepped the device-side parameters; the module's copies are behind
+        self._trainer = None             # weakref to the Trainer that owns the training state (training.py)
+        self._synced_version = None
         self.profile_events = False      # bench.py: CUDA-event time of the decode loop per inference()
         self.decode_ms = []
         self._ws = None
@@ -156,7 +159,30 @@ class TransformerTTS(nn.Module):
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)
         self._dirty = True
+        self._host_stale = False         # explicit weights win over un-exported training state
         return out
+
+    def _param_version(self):
+        """Sum of the in-place version counters of every parameter / buffer: changes whenever an optimiser, `copy_`,
+        `fill_` ... touches the module's tensors, so stale packed weights are never used silently."""
+        return sum(int(t._version) for t in self._raw_state_dict().values())
+
+    def _raw_state_dict(self):
+        return super().state_dict()
+
+    def _pull_trained_state(self):
+        """After Trainer.step() the parameters the optimiser moved live in the library's training buffers; bring them
+        back into the module before anything reads the module's tensors (inference, forward, state_dict)."""
+        if self._host_stale:
+            tr = self._trainer() if self._trainer is not None else None
+            if tr is None:
+                raise RuntimeError("the Trainer that stepped this module is gone and its state was never exported "
+                                   "(call Trainer.export_to_module() before dropping it)")
+            tr.export_to_module()
+
+    def state_dict(self, *a, **k):
+        self._pull_trained_state()
+        return super().state_dict(*a, **k)
 
     def set_option(self, key: str, value: int):
         lib = self._ensure_handle()
@@ -165,15 +191,17 @@ class TransformerTTS(nn.Module):
     def sync_weights(self):
         """Push the module's parameters through tts_load_weight / tts_finalize_weights."""
         lib = self._ensure_handle()
-        if not self._dirty:
+        self._pull_trained_state()
+        if not self._dirty and self._synced_version == self._param_version():
             return
-        for name, t in self.state_dict().items():
+        for name, t in self._raw_state_dict().items():
             if not t.is_floating_point():
                 continue                                  # num_batches_tracked
             t = t.detach().to("cpu", torch.float32).contiguous()
             self._check(lib.tts_load_weight(self._handle, name.encode(), C.c_void_p(t.data_ptr()), t.numel()), f"tts_load_weight({name})")
         self._check(lib.tts_finalize_weights(self._handle), "tts_finalize_weights")
         self._dirty = False
+        self._synced_version = self._param_version()
 
     def _workspace(self, B, S, T):
         lib = self._ensure_handle()

@@ -9,6 +9,7 @@ library's single flat gradient buffer (NCCL on GPUs; SURVEY.md 8(e): one exchang
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -45,6 +46,7 @@ class Trainer:
         model.sync_weights()
         model._check(lib.tts_train_begin(model._handle), "tts_train_begin")
         self._lib, self._h = lib, model._handle
+        model._trainer = weakref.ref(self)
         ptr, n = C.c_void_p(), C.c_int64()
         model._check(lib.tts_train_grads(self._h, C.byref(ptr), C.byref(n)), "tts_train_grads")
         self.flat_grads = torch.as_tensor(_DevBuf(ptr.value, n.value), device=model.device)      # view, no copy
@@ -113,7 +115,10 @@ class Trainer:
     def adam_step(self):
         rc = self._lib.tts_train_adam(self._h, self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.world_size, self.model._stream())
         self.model._check(rc, "tts_train_adam")
-        self.model._dirty = True          # the module's host copies are stale until export_to_module()
+        # The module's host copies are now behind the device-side parameters.  They are NOT re-staged from the host (that
+        # would silently evaluate the un-trained weights): the next inference() / forward() / state_dict() on the module
+        # pulls the trained state back first (TransformerTTS._pull_trained_state -> export_to_module).
+        self.model._host_stale = True
 
     def adam_step_peers(self):
         """reduce-scatter + Adam + all-gather in one kernel over NVLink peer memory, bracketed by stream-ordered barriers."""
@@ -122,7 +127,7 @@ class Trainer:
         m._check(self._lib.tts_train_adam_peers(self._h, self.lr, self.betas[0], self.betas[1], self.eps, m._stream()), "tts_train_adam_peers")
         self._stream_barrier()                     # every shard of the new parameters has landed in every rank's buffer
         m._check(self._lib.tts_train_repack(self._h, m._stream()), "tts_train_repack")
-        m._dirty = True
+        m._host_stale = True
 
     def step(self, phonemes, phoneme_lens, mels, mel_lens, seed: int = 0, utt_offset: int = 0) -> torch.Tensor:
         loss = self.forward_backward(phonemes, phoneme_lens, mels, mel_lens, seed, utt_offset)
@@ -143,7 +148,7 @@ class Trainer:
         return mb, ma, st
 
     def _read(self, which: int) -> Dict[str, torch.Tensor]:
-        shapes = {k: v.shape for k, v in self.model.state_dict().items()}
+        shapes = {k: v.shape for k, v in self.model._raw_state_dict().items()}
         out = {}
         for name, off, numel, isb in self._table:
             if isb != (which == 2):
@@ -164,7 +169,9 @@ class Trainer:
 
     def export_to_module(self):
         """Copy the trained parameters and BatchNorm statistics back into the nn.Module (for inference / state_dict())."""
-        sd = self.model.state_dict()
-        for k, v in {**self.parameters(), **self.buffers()}.items():
-            sd[k].copy_(v)
+        sd = self.model._raw_state_dict()
+        with torch.no_grad():
+            for k, v in {**self.parameters(), **self.buffers()}.items():
+                sd[k].copy_(v)
+        self.model._host_stale = False
         self.model._dirty = True

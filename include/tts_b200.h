@@ -67,6 +67,7 @@ int tts_finalize_weights(TtsHandle* h);
 /* ---- options ---------------------------------------------------------------------------------- */
 /* "cluster_group": utterances per 8-CTA cluster of the decode kernel, 1..5 (0 = auto: as few as the number of
  *   co-resident clusters allows);  "decode_timestamps": 1 record per-phase timestamps (tts_debug_phase_timestamps);
+ *   "decode_debug": 1 dump layer-0 activations of the first step (tts_debug_read_dump);
  *   "train_graph": 1 (default) replay tts_train_step from a CUDA graph captured on the second step of a shape, 0 eager;
  *   "print_info": print device / cluster geometry to stderr. */
 int tts_set_option(TtsHandle* h, const char* key, int64_t value);
@@ -109,6 +110,10 @@ int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* 
 /* Profiling aid: with option "decode_timestamps" = 1 the persistent decode kernel stamps %globaltimer
  * after every phase; this copies [n_steps][n_phases] stamps (ns) to the host and returns n_phases. [sync] */
 int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long long* out, int n_steps, void* stream);
+/* Debugging aid: with option "decode_debug" = 1 cluster 0 / CTA 0 of the decode kernel dumps the activations of the group's
+ * rows after the prenet and after every sub-layer of decoder layer 0 at the first step of each launch (slots of 2560 floats,
+ * see decode_cluster.cuh: dbg_dump); this copies `n` floats starting at float `offset` of that dump to the host. [sync] */
+int tts_debug_read_dump(TtsHandle* h, void* ws, int64_t offset, int64_t n, float* out_host, void* stream);
 
 /* ---- training step (oracle: TransformerTTS.forward in .train() mode + tts_loss + autograd + torch.optim.Adam;
  *      oracle/transformer_tts.py:forward, :tts_loss, :masked_batchnorm) ---------------- */

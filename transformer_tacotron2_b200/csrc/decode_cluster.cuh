@@ -1,27 +1,32 @@
 // Cluster-partitioned autoregressive decode: the north-star hot loop.
 //
-// Utterances are independent end to end, so the batch is cut into groups of up to 8 utterances and
-// each group is decoded by ONE thread-block cluster of 8 CTAs (CTA r owns attention head r) with no
-// grid-wide synchronisation at all:
-//   * every GEMM of the step is split over the 8 CTAs along N (FFN2 along K); the <= 8 utterances
-//     are the MMA n = 8 dimension ("swap-AB": weights are the 16x16 A operand of
-//     mma.sync.m16n8k16, activations the 16x8 B operand), so a weight byte is read once per cluster
-//     and the accumulators of a warp stay in registers across the whole K loop;
-//   * results are exchanged through distributed shared memory (16-byte st.shared::cluster pushes)
-//     and ordered by an mbarrier-based cluster barrier (remote arrive.release / local
-//     try_wait.acquire), ~40 per step instead of 52 grid barriers;
+// Utterances are independent end to end, so the batch is cut into groups of up to 5 utterances and each group is decoded
+// by ONE thread-block cluster of 8 CTAs (CTA r owns attention head r) with no grid-wide synchronisation at all:
+//   * every GEMM of the step is split over the 8 CTAs along N (FFN2 along K); the <= 5 utterances are the MMA n = 8
+//     dimension ("swap-AB": weights are the 16x16 A operand of mma.sync.m16n8k16, activations the 16x8 B operand);
+//   * results are exchanged through distributed shared memory: 16-byte st.async pushes that complete a transaction
+//     count on the RECEIVER's mbarrier (one DSMEM latency per exchange, no separate arrive / wait round);
 //   * LayerNorm, residuals, dropout, PE and the stop test run on the gathered rows in shared memory;
-//   * ALL global traffic of a CTA -- its 1/8 slice of the weights and the K/V rows of its 8
-//     (utterance, head) pairs -- is one ordered stream of cp.async.bulk copies into a 4 x 32 KB
-//     shared-memory ring (mbarrier full/empty), issued by a dedicated producer warp that keeps 96 KB
-//     in flight per SM (profiles/r01_bulk_bw_ubench.md: what one SM needs to pull > 100 GB/s).
-// Weights are packed per CTA rank in exactly the order the step consumes them (tts_b200.cu), each
-// 16(n) x 32(k) block in A-fragment order, blocks ordered [chunk][warp][2].
-// KV-cache layout (P18, adapted to the tensor-core decode attention): per (layer, b, h) and padded length
-// Lp = roundup(L, 16):  K row-major [Lp][64];  V in 16-row blocks stored transposed [Lp/16][64 d][16 rows],
-// so that a 16-row chunk of either is one contiguous 2 KB bulk copy and both are A operands of
-// mma.sync.m16n8k16 straight from shared memory with conflict-free 16-/8-byte loads (the k index of an
-// MMA may be permuted freely as long as A and B agree).
+//   * ALL global traffic of a CTA -- its 1/8 slice of the weights and the K/V rows of its (utterance, head) pairs -- is
+//     one ordered stream of cp.async.bulk copies into a 5 x 32 KB shared-memory ring (mbarrier full / empty).
+//
+// Round 2 (profiles/r02_ring_ubench.md): the ring is bound by a FIXED COST PER CHUNK HAND-OFF (producer ~0.16 us per copy
+// when one lane runs the loop alone, ~0.35 us when a whole warp loops; a consumer warp ~0.28 us per wait -> release round),
+// not by bytes.  So:
+//   * the producer is ONE elected lane;
+//   * a stage is read only by the warps that own its contents.  GEMMs: warp w owns output tile(s) w over the WHOLE local
+//     K; its weights are one contiguous run (16 KB for K = 512) and a 32 KB stage carries the runs of consecutive warps
+//     -- a warp waits ONCE per GEMM and no K-split reduction through shared memory exists any more.  Attention: a stage
+//     is 128 cache rows of ONE (utterance, head) pair, read by that pair's 3 warps;
+//   * the K/V cache is laid out in 64-row blocks with K and V interleaved, so 128 rows of a pair are ONE 32 KB copy
+//     (the copy engine needs ~44 ns per separate piece: the round-1 chunk of 2 x G pieces of 2 KB ran at 41 GB/s per SM).
+//
+// KV-cache layout (P18, adapted): per (layer, utterance, head) a run of 64-row blocks, 16 KB each:
+//     [ K rows 0..63 row-major [64][64] bf16 | V in four 16-row sub-blocks, each stored transposed [64 d][16 rows] ]
+// Both halves are A operands of mma.sync.m16n8k16 straight from shared memory with conflict-free 16- / 8-byte loads
+// (the k index of an MMA may be permuted freely as long as A and B agree).
+// Weights are packed per CTA rank in exactly the order the step consumes them (tts_b200.cu: pack_cluster_segment), each
+// 16(n) x 32(k) block in A-fragment order.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -30,11 +35,20 @@
 namespace tts {
 
 constexpr int CL_SIZE = 8, CL_CONSUMERS = 512, CL_THREADS = 544, CL_WARPS = 16;
-// Row capacity of a cluster.  5 rather than the MMA's 8: the activation buffers shrink by 35 KB, which buys a fifth
-// 32 KB ring stage (128 KB instead of 96 KB in flight per SM); B = 64 still fits one pass (13 clusters of <= 15).
+// Row capacity of a cluster.  5: at most 15 8-CTA clusters of this kernel are co-resident on a B200 (120 SMs), so B = 64 is
+// 13 groups of <= 5; the activation buffers of 5 rows leave room for five 32 KB ring stages.
 constexpr int CL_G = 5;
-constexpr int CL_STAGES = 5, CL_STAGE_BYTES = 32768, CL_KV_ROWS = 16;   // K/V chunk: 16 rows of every pair of the CTA
+constexpr int CL_STAGES = 5, CL_STAGE_BYTES = 32768;
+// `full` barriers: two per ring slot, used alternately (stage idx -> barrier idx % 10, parity (idx / 10) & 1).  A warp waits only
+// on the stages it reads, so it can reach its wait before the PREVIOUS use of the slot has landed; with one barrier per slot
+// the one-bit parity test would then pass on the use before that (same parity) and the warp would read stale bytes.  With two,
+// the test can only be fooled by a warp >= 10 stages ahead of the landed data, and the block-wide barriers after every
+// segment (and the in-order waits inside an attention segment: G + 5 <= 10) keep every reader closer than that.
+constexpr int CL_FULL_BARS = 2 * CL_STAGES;
 constexpr int CL_NS = 512 / CL_SIZE;                 // 64: columns of a 512-wide output owned by one rank
+constexpr int KV_BLOCK_ROWS = 64, KV_BLOCK_ELEMS = 8192;     // one cache block: 64 rows of K + 64 rows of V = 16 KB
+constexpr int KV_STAGE_ROWS = 128;                   // rows of one pair per ring stage (two blocks)
+constexpr int ATT_WPP = 3;                           // warps per (utterance, head) pair: sub-chunk c of 16 rows -> warp c % 3
 
 // bytes of one rank's packed weight segments (stream order: fc1 fc2 proj | 6 x (qkv o q2 o2 w1 w2) | head)
 constexpr int CLW_FC1 = 8 * 1024, CLW_FC2 = 16 * 1024, CLW_PROJ = 32 * 1024;
@@ -45,9 +59,9 @@ constexpr size_t CLW_RANK_BYTES = (size_t)CLW_FC1 + CLW_FC2 + CLW_PROJ + 6 * (si
 // shared memory carve-up (bytes)
 constexpr int SM_RING = 0;
 constexpr int SM_XRES = SM_RING + CL_STAGES * CL_STAGE_BYTES;   // f32 [G][512]  residual stream
-constexpr int SM_YBUF = SM_XRES + CL_G * 2048;                  // f32 [G][512]  gathered pre-LN sums / FFN2 partial staging
-constexpr int SM_RECV = SM_YBUF + CL_G * 2048;                  // f32 [8 ranks][G][64] FFN2 reduce-scatter; epilogue staging otherwise
-constexpr int SM_RED = SM_RECV + CL_G * 2048;                   // f32 [16][128] K-split partials; [4096, 8192): LayerNorm gamma | beta
+constexpr int SM_YBUF = SM_XRES + CL_G * 2048;                  // f32 [G][512]  gathered pre-LN sums / FFN2 partial sums
+constexpr int SM_RECV = SM_YBUF + CL_G * 2048;                  // f32 [8 ranks][G][64] FFN2 reduce-scatter; per-warp epilogue staging otherwise
+constexpr int SM_RED = SM_RECV + CL_G * 2048;                   // [0, 4096): attention output staging; [4096, 8192): LayerNorm gamma | beta
 constexpr int SM_XA = SM_RED + 8192;                            // bf16 [G][520] LN output as MMA operand
 constexpr int SM_ABUF = SM_XA + CL_G * 1040;                    // bf16 [G][520] gathered attention outputs (prenet: h2 [G][264])
 constexpr int SM_QKV = SM_ABUF + CL_G * 1040;                   // f32 [G][192]  q | k_t | v_t of this head
@@ -55,9 +69,9 @@ constexpr int SM_HBUF = SM_QKV + CL_G * 768;                    // bf16 [G][264]
 constexpr int SM_H1 = SM_HBUF + CL_G * 528;                     // bf16 [G][264] gathered prenet activations
 constexpr int SM_H2 = SM_ABUF;                                  // aliases abuf (idle during the prenet)
 constexpr int SM_FBUF = SM_H1 + CL_G * 528;                     // bf16 [G][136] previous frame (K padded to 128)
-constexpr int SM_AMERGE = SM_FBUF + CL_G * 272;                 // f32 [16][68]  attention warp scratch
-constexpr int SM_MISC = SM_AMERGE + 4352;                       // mbarriers + flags + head records
-constexpr int CL_SMEM_BYTES = SM_MISC + 320;
+constexpr int SM_AMERGE = SM_FBUF + CL_G * 272;                 // f32 [16][68]  attention partials (m, l, o[64]) per warp
+constexpr int SM_MISC = SM_AMERGE + 4352;                       // mbarriers + flags + head records + group lengths
+constexpr int CL_SMEM_BYTES = SM_MISC + 384;                    // 17 mbarriers (136 B) | flags @192 | hrec @224 | glens @352
 static_assert(CL_SMEM_BYTES <= 232448, "decode kernel shared memory exceeds 227 KB");
 // (MMA B fragments are loaded with ldmatrix over 8 rows: rows >= G read whatever follows the buffer -- finite or not, they
 //  only feed output columns m >= G, which are never used.)
@@ -67,22 +81,27 @@ struct ClusterLayerParams {
     const float *bqkv, *bo, *bq2, *bo2, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b, *ln3g, *ln3b;
 };
 struct ClusterParams {
-    // TMA descriptors of the two K/V caches viewed as 4-D bf16 tensors [12*B (layer,kv,b)][8 h][Lpad rows][64]:
-    // one box {64, 16, 1, G} = the 16-row chunk of all G utterances of a cluster for one head, in one copy
-    alignas(64) CUtensorMap tm_self;
-    alignas(64) CUtensorMap tm_cross;
-    int B, Tmax, S, G, ngroups;                  // G utterances per cluster (<= 8)
-    int Tpad, Spad;                              // cache row capacities, multiples of 16
+    int B, Tmax, S, G, ngroups;                  // G utterances per cluster (<= CL_G)
+    int nblk_self, nblk_cross;                   // 64-row blocks per (layer, utterance, head) in the two caches
     uint64_t seed; int utt_offset; float dec_alpha; float ln_eps; const float* pe;
     const unsigned char* wpack;                  // [8][CLW_RANK_BYTES]
     const float *b_fc1, *b_fc2, *b_proj, *b_head;
     ClusterLayerParams layer[6];
-    bf16* self_kv;                               // [6][2][B][8][Tpad*64]  (K row-major, V blocked-transposed)
-    const bf16* cross_kv;                        // [6][2][B][8][Spad*64]
+    bf16* self_kv;                               // [6][B][8][nblk_self][KV_BLOCK_ELEMS]
+    const bf16* cross_kv;                        // [6][B][8][nblk_cross][KV_BLOCK_ELEMS]
     const int* plens;
     float* mel_before; float* stop_logits; int* lens; int* finished; int* n_finished;
     unsigned long long* ts;                      // optional [Tmax][64] %globaltimer stamps (cluster 0, rank 0)
+    int dbg_rank;
+    float* dbg;                                  // optional debug dump (cluster 0, rank dbg_rank, first step of the launch): slots of 2560 floats
 };
+// element offset of cache block `blk` of (layer, utterance, head)
+TTS_HD size_t kv_block_offset(int layer, int B, int b, int h, int nblk, int blk) {
+    return ((((size_t)layer * B + b) * kHeads + h) * nblk + blk) * KV_BLOCK_ELEMS;
+}
+// element offsets of row r (0..63) inside a block: K row-major, V in transposed 16-row sub-blocks
+TTS_HD int kv_k_elem(int r, int d) { return r * kDHead + d; }
+TTS_HD int kv_v_elem(int r, int d) { return KV_BLOCK_ELEMS / 2 + (r >> 4) * 1024 + d * 16 + (r & 15); }
 
 // ---------------------------------------------------------------- PTX helpers
 TTS_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,10 +132,6 @@ TTS_D bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 TTS_D void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
-TTS_D void tma_g2s_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar, uint64_t policy) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
-                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
 TTS_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
@@ -128,89 +143,97 @@ struct ClCtx {
     uint64_t *full, *empty, *gsync;           // ring full/empty, data-carrying gather barriers [2]
     int rank, tid, warp, lane;
     int b0, G;                           // group base utterance, rows in this group
-    uint32_t consumed;                   // chunks consumed (uniform over the consumer warps)
+    uint32_t consumed;                   // ring stages consumed or skipped so far (uniform over the consumer warps)
     uint32_t gphase;                     // gather phase counter (40 per decoder step)
 };
 
-// The ordered stream of chunks of one step for one rank.  seg: 0 fc1, 1 fc2, 2 proj,
-// 3+8l+{0 qkv, 1 self-KV, 2 o, 3 q2, 4 cross-KV, 5 o2, 6 w1, 7 w2}, 51 head.
-TTS_D int seg_chunks(int seg, int t, int S, int G, int rank) {
-    if (seg < 3) return 1;
-    if (seg == 51) return rank < 6 ? 1 : 0;
+// ---------------------------------------------------------------- the stage stream of one step (shared by producer and consumers)
+// seg: 0 fc1, 1 fc2, 2 proj, 3+8l+{0 qkv, 1 self-KV, 2 o, 3 q2, 4 cross-KV, 5 o2, 6 w1, 7 w2}, 51 head.
+// A weight segment is `total` bytes for `na` warps, `bw` bytes each, 32768 / bw warps per stage.
+struct WSeg { int total, bw, na; };
+TTS_D WSeg wseg(int seg, int rank) {
+    if (seg == 0) return {CLW_FC1, 4096, 2};
+    if (seg == 1) return {CLW_FC2, 8192, 2};
+    if (seg == 2) return {CLW_PROJ, 8192, 4};
+    if (seg == 51) return {rank < 6 ? CLW_HEAD : 0, 16384, rank < 6 ? 1 : 0};
     switch ((seg - 3) & 7) {
-    case 0: case 6: case 7: return 8;
-    case 1: return (t + CL_KV_ROWS - 1) / CL_KV_ROWS;
-    case 4: return (S + CL_KV_ROWS - 1) / CL_KV_ROWS;
-    default: return 2;
+    case 0: return {CLW_QKV, 16384, 12};
+    case 6: return {CLW_W1, 16384, 16};
+    case 7: return {CLW_W2, 16384, 16};
+    default: return {CLW_O, 16384, 4};
     }
-}
-// consumer warps that read a chunk of segment `seg` (the producer arrives on the slot's empty barrier for the others,
-// so warps that do not need a chunk never touch it and a slot is free again as soon as its readers have loaded it)
-TTS_D int seg_readers(int seg, int G) {
-    if (seg == 0) return 4;
-    if (seg == 1 || seg == 51) return 8;
-    if (seg == 2) return 16;
-    switch ((seg - 3) & 7) {
-    case 0: return 12;
-    case 1: case 4: return G;                      // one warp per (utterance, head) pair and chunk
-    default: return 16;
-    }
-}
-TTS_D uint32_t seg_weight_bytes(int seg) {          // bytes per chunk of a weight segment
-    if (seg == 0) return CLW_FC1;
-    if (seg == 1) return CLW_FC2;
-    if (seg == 51) return CLW_HEAD;
-    if (seg >= 3 && ((seg - 3) & 7) == 0) return CLW_QKV / 8;
-    return CL_STAGE_BYTES;
 }
 
-// Producer warp: issue the whole chunk stream of steps [t0, t_end) in order, each chunk as soon as its ring
-// slot has been released by all 16 consumer warps.  Weight chunks are one bulk copy; a K/V chunk is two TMA
-// tensor copies (the 16-row K box and the V block box of all G pairs): separate <= 2 KB bulk copies cost ~50 ns
-// each in the copy engine (profiles/r01_bulk_bw_ubench.md) and capped the stream at ~40 GB/s per SM.  Stops early when the
-// consumers raise flags[1].  The control flow is warp-uniform.
+// Producer: ONE lane issues the whole stage stream of steps [t0, t_end) in order, each stage as soon as its ring slot has
+// been released (the other 31 lanes of the warp park at the group-end barrier).  A weight stage is one bulk copy; a K/V
+// stage is one copy (128 full rows) or up to three (the last, partial stage of a pair, at 16-row granularity).  It arrives
+// on the slot's empty barrier on behalf of the warps that do not read the stage.  Stops early when the consumers raise flags[1].
 TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* full, uint64_t* empty, volatile int* flags,
-                       int rank, int b0, int G, int t0, int t_end, int lane) {
-    // ONE lane runs the whole loop alone (the other 31 go straight to the group-end barrier): a warp-wide loop with
-    // lane-0-predicated copies and a __syncwarp per chunk costs ~0.35 us per chunk, a lone lane ~0.16 us
-    // (scripts/ubench/ring_bisect2.cu, profiles/r02_ring_ubench.md) -- the difference between 90 and 200 GB/s per SM.
-    if (lane != 0) return;
+                       const volatile int* glens, int rank, int b0, int G, int t0, int t_end) {
     const uint64_t pol_w = l2_policy_evict_last(), pol_kv = l2_policy_evict_first();
     uint32_t issued = 0;
     const unsigned char* wbase = p.wpack + (size_t)rank * CLW_RANK_BYTES;
     bool stopped = false;
+    uint64_t* fbar = nullptr;                            // full barrier of the stage being issued
+    auto slot = [&](uint32_t& stage) -> bool {           // wait until ring slot issued % STAGES is free
+        stage = issued % CL_STAGES;
+        fbar = &full[issued % CL_FULL_BARS];
+        const uint32_t use = issued / CL_STAGES;
+        if (use > 0)
+            while (!mbar_try_wait(&empty[stage], (use & 1) ^ 1))
+                if (flags[1]) { stopped = true; return false; }
+        return true;
+    };
     for (int t = t0; t < t_end && !stopped; ++t) {
         size_t woff = 0;
         for (int seg = 0; seg <= 51 && !stopped; ++seg) {
-            const int n = seg_chunks(seg, t, p.S, G, rank);
             const int sub = (seg < 3 || seg == 51) ? -1 : ((seg - 3) & 7);
-            for (int i = 0; i < n; ++i) {
-                const int stage = issued % CL_STAGES;
-                const uint32_t use = issued / CL_STAGES;
-                if (use > 0) {
-                    while (!mbar_try_wait(&empty[stage], (use & 1) ^ 1)) {
-                        if (flags[1]) { stopped = true; break; }
+            if (sub == 1 || sub == 4) {                  // K/V rows of every pair (b0 + pair, head rank), 128 rows per stage
+                const int l = (seg - 3) >> 3;
+                const bool self = sub == 1;
+                const int L = self ? t : p.S, nblk = self ? p.nblk_self : p.nblk_cross;
+                const bf16* cache = self ? p.self_kv : p.cross_kv;
+                const int nj = (L + KV_STAGE_ROWS - 1) / KV_STAGE_ROWS;
+                for (int j = 0; j < nj && !stopped; ++j)
+                    for (int pair = 0; pair < G; ++pair) {
+                        uint32_t stage;
+                        if (!slot(stage)) break;
+                        unsigned char* dst = smem + SM_RING + stage * CL_STAGE_BYTES;
+                        const int Lb = self ? t : min(L, glens[pair]);
+                        const int rows = max(0, min(KV_STAGE_ROWS, Lb - j * KV_STAGE_ROWS));
+                        const int r16 = (rows + 15) & ~15;
+                        const bf16* src = cache + kv_block_offset(l, p.B, b0 + pair, rank, nblk, 2 * j);
+                        if (r16 == 0) mbar_arrive(fbar);
+                        else {
+                            mbar_expect_tx(fbar, (uint32_t)r16 * 256u);
+                            if (r16 == KV_STAGE_ROWS) bulk_g2s(dst, src, 32768u, fbar, pol_kv);
+                            else {
+                                int rem = r16, off = 0;
+                                if (rem >= KV_BLOCK_ROWS) { bulk_g2s(dst, src, 16384u, fbar, pol_kv); rem -= KV_BLOCK_ROWS; off = 16384; }
+                                if (rem > 0) {
+                                    const unsigned char* s2 = reinterpret_cast<const unsigned char*>(src) + off;
+                                    bulk_g2s(dst + off, s2, (uint32_t)rem * 128u, fbar, pol_kv);
+                                    bulk_g2s(dst + off + 8192, s2 + 8192, (uint32_t)rem * 128u, fbar, pol_kv);
+                                }
+                            }
+                        }
+                        mbar_arrive_n(&empty[stage], (uint32_t)(CL_WARPS - ATT_WPP));
+                        ++issued;
                     }
-                    if (stopped) break;
-                }
-                unsigned char* dst = smem + SM_RING + stage * CL_STAGE_BYTES;
-                if (sub == 1 || sub == 4) {                      // 16 K rows + one V block of every pair (b0.., head rank): 2 TMA boxes
-                    const int l = (seg - 3) >> 3;
-                    const CUtensorMap* tm = sub == 1 ? &p.tm_self : &p.tm_cross;
-                    mbar_expect_tx(&full[stage], 2u * (uint32_t)p.G * 2048u);
-                    tma_g2s_4d(dst, tm, 0, i * CL_KV_ROWS, rank, (l * 2) * p.B + b0, &full[stage], pol_kv);
-                    tma_g2s_4d(dst + 16384, tm, 0, i * CL_KV_ROWS, rank, (l * 2 + 1) * p.B + b0, &full[stage], pol_kv);
-                } else {
-                    const uint32_t bytes = seg_weight_bytes(seg);
-                    mbar_expect_tx(&full[stage], bytes);
-                    bulk_g2s(dst, wbase + woff, bytes, &full[stage], pol_w);
+            } else {
+                const WSeg ws = wseg(seg, rank);
+                const int wps = CL_STAGE_BYTES / ws.bw;
+                for (int done = 0, w0 = 0; done < ws.total; done += CL_STAGE_BYTES, w0 += wps) {
+                    uint32_t stage;
+                    if (!slot(stage)) break;
+                    const uint32_t bytes = (uint32_t)min(CL_STAGE_BYTES, ws.total - done);
+                    const int readers = min(wps, ws.na - w0);
+                    mbar_expect_tx(fbar, bytes);
+                    bulk_g2s(smem + SM_RING + stage * CL_STAGE_BYTES, wbase + woff, bytes, fbar, pol_w);
                     woff += bytes;
+                    mbar_arrive_n(&empty[stage], (uint32_t)(CL_WARPS - readers));
+                    ++issued;
                 }
-                {
-                    const int nskip = CL_WARPS - seg_readers(seg, G);
-                    if (nskip > 0) mbar_arrive_n(&empty[stage], (uint32_t)nskip);
-                }
-                ++issued;
             }
         }
     }
@@ -218,110 +241,83 @@ TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* fu
     while (!flags[1]) {}
     __threadfence_block();
     const uint32_t final_consumed = (uint32_t)flags[2];
-    for (uint32_t i = final_consumed; i < issued; ++i) mbar_wait(&full[i % CL_STAGES], (i / CL_STAGES) & 1);
+    for (uint32_t i = final_consumed; i < issued; ++i) mbar_wait(&full[i % CL_FULL_BARS], (i / CL_FULL_BARS) & 1);
 }
 
-TTS_D unsigned char* cl_acquire(ClCtx& c) {
-    const int stage = c.consumed % CL_STAGES;
-    // every lane polls: a single polling lane with the rest parked at __syncwarp wakes up ~2x slower
-    // (scripts/ubench/pipe_rtt.cu: 0.57 -> 0.32 us per 32 KB chunk)
-    mbar_wait(&c.full[stage], (c.consumed / CL_STAGES) & 1);
+// ring stage `idx` (absolute index in the stream): wait until it has landed / hand it back
+TTS_D const unsigned char* cl_acquire(const ClCtx& c, uint32_t idx) {
+    const uint32_t stage = idx % CL_STAGES;
+    mbar_wait(&c.full[idx % CL_FULL_BARS], (idx / CL_FULL_BARS) & 1);    // all lanes poll: the fastest wake-up for a whole warp (r02_ring_ubench.md)
     return c.smem + SM_RING + stage * CL_STAGE_BYTES;
 }
-TTS_D void cl_release(ClCtx& c) {
+TTS_D void cl_release(const ClCtx& c, uint32_t idx) {
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(&c.empty[c.consumed % CL_STAGES]);
-    ++c.consumed;
+    if (c.lane == 0) mbar_arrive(&c.empty[idx % CL_STAGES]);
 }
 
-// ---------------------------------------------------------------- GEMM over ring chunks
-// out[col = tile*16 + n][m] = sum_k W[col][k] * X[m][k].  Each of the first NT*KSPLIT warps owns tile
-// (w % NT) and K-slice (w / NT) and consumes blocks 2w, 2w+1 of every chunk (k-pairs kq*2*nchunks + 2c + j);
-// typeB (FFN2): warp w owns tiles 2w, 2w+1 and chunk c carries k-pair c of both.  Accumulators stay in
-// registers across chunks; K-split partials are reduced once per segment through shared memory.
-template <class BiasFn, class Epi>
-TTS_D void cl_gemm(ClCtx& c, int nchunks, int NT, int KSPLIT, bool typeB, const bf16* X, int ldx, BiasFn biasf, Epi epi) {
-    const int nactive = typeB ? CL_WARPS : NT * KSPLIT;
-    const bool active = c.warp < nactive;
-    const int kq = typeB ? 0 : c.warp / NT;
-    const int g = c.lane >> 2, t4 = c.lane & 3;
-    const bool direct = typeB || KSPLIT == 1;            // complete sums end up in registers
-    // biases (global memory) are fetched before the first chunk arrives, off the critical path
-    float bias[4] = {0.f, 0.f, 0.f, 0.f};
-    if (direct) {
-        if (active) {
-            const int tile0 = typeB ? c.warp * 2 : c.warp;
-            bias[0] = biasf(tile0, g); bias[1] = biasf(tile0, g + 8);
-            if (typeB) { bias[2] = biasf(tile0 + 1, g); bias[3] = biasf(tile0 + 1, g + 8); }
-        }
-    } else {
+// ---------------------------------------------------------------- GEMM: one warp = TW output tiles x the whole local K
+// out[col = tile*16 + n][m] = sum_k W[col][k] * X[m][k] for tiles warp*TW .. warp*TW + TW-1, K = 32*KP.  The warp's weights are one
+// contiguous run of TW*KP KB ([kp][j] blocks of 1 KB) inside a ring stage shared with its neighbours; the accumulators never leave
+// registers (NCH independent MMA chains per tile).  epi(tile, n, m, value) receives complete sums (+ bias).  No block-level
+// barrier inside: callers synchronise where the results are consumed.
+template <int KP, int TW, class BiasFn, class Epi>
+TTS_D void cl_gemm(ClCtx& c, int na, const bf16* X, int ldx, BiasFn biasf, Epi epi) {
+    constexpr int BW = TW * KP * 1024, WPS = CL_STAGE_BYTES / BW;
+    constexpr int NCH = (TW == 1 && KP >= 16) ? 4 : 2;
+    const int nst = (na + WPS - 1) / WPS;
+    if (c.warp < na) {
+        const int g = c.lane >> 2, t4 = c.lane & 3;
+        float bias[TW][2];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int o = c.tid + k * CL_CONSUMERS;
-            if (o < NT * 128) bias[k] = biasf(o >> 7, (o >> 3) & 15);
-        }
-    }
-    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-    if (!active) c.consumed += nchunks;                  // the producer released these chunks on my behalf
-    else
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const unsigned char* st = cl_acquire(c);
-        {
+        for (int j = 0; j < TW; ++j) { bias[j][0] = biasf(c.warp * TW + j, g); bias[j][1] = biasf(c.warp * TW + j, g + 8); }
+        float acc[TW][NCH][4];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int bi = c.warp * 2 + j;
-                const int kp = typeB ? ch : kq * 2 * nchunks + 2 * ch + j;
-                const uint4 w0 = reinterpret_cast<const uint4*>(st)[(bi * 2) * 32 + c.lane];
-                const uint4 w1 = reinterpret_cast<const uint4*>(st)[(bi * 2 + 1) * 32 + c.lane];
-                uint32_t bfrag[4];
-                ldmatrix_x4(bfrag, X + (c.lane & 7) * ldx + kp * 32 + (c.lane >> 3) * 8);
+        for (int j = 0; j < TW; ++j)
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) { acc[j][q][0] = acc[j][q][1] = acc[j][q][2] = acc[j][q][3] = 0.f; }
+        const uint32_t idx = c.consumed + (uint32_t)(c.warp / WPS);
+        const uint4* wp = reinterpret_cast<const uint4*>(cl_acquire(c, idx) + (c.warp % WPS) * BW);
+        const bf16* xrow = X + (c.lane & 7) * ldx + (c.lane >> 3) * 8;
+#pragma unroll
+        for (int kp = 0; kp < KP; ++kp) {
+            uint32_t bfrag[4];
+            ldmatrix_x4(bfrag, xrow + kp * 32);
+#pragma unroll
+            for (int j = 0; j < TW; ++j) {
+                const uint4 w0 = wp[((kp * TW + j) * 2) * 32 + c.lane];
+                const uint4 w1 = wp[((kp * TW + j) * 2 + 1) * 32 + c.lane];
                 const uint32_t a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w};
-                if (typeB && j == 1) { mma_bf16_16816(acc1, a0, bfrag[0], bfrag[1]); mma_bf16_16816(acc1, a1, bfrag[2], bfrag[3]); }
-                else { mma_bf16_16816(acc0, a0, bfrag[0], bfrag[1]); mma_bf16_16816(acc0, a1, bfrag[2], bfrag[3]); }
+                mma_bf16_16816(acc[j][kp % NCH], a0, bfrag[0], bfrag[1]);
+                mma_bf16_16816(acc[j][kp % NCH], a1, bfrag[2], bfrag[3]);
             }
         }
-        cl_release(c);
-    }
-    if (direct) {
-        if (active) {
-            const int tile0 = typeB ? c.warp * 2 : c.warp;
-            const int m0 = t4 * 2;
-            if (m0 < c.G) { epi(tile0, g, m0, acc0[0] + bias[0]); epi(tile0, g + 8, m0, acc0[2] + bias[1]); }
-            if (m0 + 1 < c.G) { epi(tile0, g, m0 + 1, acc0[1] + bias[0]); epi(tile0, g + 8, m0 + 1, acc0[3] + bias[1]); }
-            if (typeB) {
-                if (m0 < c.G) { epi(tile0 + 1, g, m0, acc1[0] + bias[2]); epi(tile0 + 1, g + 8, m0, acc1[2] + bias[3]); }
-                if (m0 + 1 < c.G) { epi(tile0 + 1, g, m0 + 1, acc1[1] + bias[2]); epi(tile0 + 1, g + 8, m0 + 1, acc1[3] + bias[3]); }
-            }
-        }
-        consumer_bar();
-    } else {
-        float* red = reinterpret_cast<float*>(c.smem + SM_RED);
-        if (active) {
-            float* r = red + c.warp * 128;
-            *reinterpret_cast<float2*>(r + g * 8 + t4 * 2) = make_float2(acc0[0], acc0[1]);
-            *reinterpret_cast<float2*>(r + (g + 8) * 8 + t4 * 2) = make_float2(acc0[2], acc0[3]);
-        }
-        consumer_bar();
+        cl_release(c, idx);
+        const int m0 = t4 * 2;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int o = c.tid + k * CL_CONSUMERS;
-            if (o < NT * 128) {
-                const int ti = o >> 7, n = (o >> 3) & 15, m = o & 7;
-                float v = bias[k];
-                for (int q = 0; q < KSPLIT; ++q) v += red[(q * NT + ti) * 128 + n * 8 + m];     // fixed order: deterministic
-                if (m < c.G) epi(ti, n, m, v);
+        for (int j = 0; j < TW; ++j) {
+            float s[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float v = acc[j][0][e];
+#pragma unroll
+                for (int q = 1; q < NCH; ++q) v += acc[j][q][e];           // fixed order: deterministic
+                s[e] = v;
             }
+            const int tile = c.warp * TW + j;
+            if (m0 < c.G) { epi(tile, g, m0, s[0] + bias[j][0]); epi(tile, g + 8, m0, s[2] + bias[j][1]); }
+            if (m0 + 1 < c.G) { epi(tile, g, m0 + 1, s[1] + bias[j][0]); epi(tile, g + 8, m0 + 1, s[3] + bias[j][1]); }
         }
-        consumer_bar();
     }
+    c.consumed += (uint32_t)nst;
 }
 
 // ---- DSMEM pushes that carry their own completion ---------------------------------------------------------------
 // Every exchange of the step ("gather phase") is a set of 16-byte st.async stores into the peers' shared memory, each
 // of which completes 16 bytes of a transaction count on the RECEIVER's mbarrier: the receiver waits for the expected
-// byte count of the phase instead of a separate arrive/wait round after the data (one DSMEM latency instead of
-// two-and-a-half).  Two barriers alternate (a peer can be at most one phase ahead, because every rank contributes to
-// every phase); barrier k&1 is re-armed for phase k+2 the moment phase k completes, so data never precedes its arming.
+// byte count of the phase instead of a separate arrive/wait round after the data.  Two barriers alternate (a peer can be
+// at most one phase ahead, because every rank contributes to every phase); barrier k&1 is re-armed for phase k+2 the moment
+// phase k completes.  (Data that overtakes the re-arming only drives the transaction count negative for a moment: the phase
+// cannot complete before the arming arrive.)
 TTS_D void st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c2, uint32_t d, uint32_t remote_bar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
                  ::"r"(addr), "r"(a), "r"(b), "r"(c2), "r"(d), "r"(remote_bar) : "memory");
@@ -335,31 +331,37 @@ TTS_D uint32_t gather_bytes(int ph, int G) {
     return (k == 0 || k == 2) ? 1024u * G : 2048u * G;   // attention outputs (bf16) : f32 slices (O, O2, reduce-scatter, y3)
 }
 TTS_D uint32_t gather_bar(const ClCtx& c) { return smem_u32(&c.gsync[c.gphase & 1]); }
-TTS_D void gather_wait(ClCtx& c) {
-    uint64_t* bar = &c.gsync[c.gphase & 1];
-    mbar_wait(bar, (c.gphase >> 1) & 1);
-    if (c.tid == 0) mbar_expect_tx(bar, gather_bytes((int)((c.gphase + 2) % 40), c.G));
+// Block-wide completion of the current gather phase: warp 0 waits on the mbarrier (one warp polling instead of sixteen),
+// re-arms it for phase + 2, and the named barrier releases everybody.
+TTS_D void gather_sync(ClCtx& c) {
+    if (c.warp == 0) {
+        uint64_t* bar = &c.gsync[c.gphase & 1];
+        mbar_wait(bar, (c.gphase >> 1) & 1);
+        if (c.lane == 0) mbar_expect_tx(bar, gather_bytes((int)((c.gphase + 2) % 40), c.G));
+    }
+    consumer_bar();
     ++c.gphase;
 }
-// dst (f32, row stride dld) of every peer <- stage[m][0..ncols)
-TTS_D void push_f32_all(const ClCtx& c, const float* stage, int ld, float* dst, int dld, int ncols) {
-    const int ppr = ncols >> 2, per_peer = c.G * ppr;
+// One warp pushes rows [0, G) x 16 fp32 columns of its private staging tile (row stride 16 floats) to dst[m][0..16)
+// (row stride dld) of every peer.
+TTS_D void push_tile_f32(const ClCtx& c, const float* wst, float* dst, int dld) {
     const uint32_t bar = gather_bar(c);
-    for (int i = c.tid; i < per_peer * CL_SIZE; i += CL_CONSUMERS) {
-        const int peer = i / per_peer, j = i % per_peer, m = j / ppr, pc = j - m * ppr;
-        const float4 v = *reinterpret_cast<const float4*>(stage + m * ld + pc * 4);
+    const int per_peer = c.G * 4;
+    for (int i = c.lane; i < per_peer * CL_SIZE; i += 32) {
+        const int peer = i / per_peer, j = i - peer * per_peer, m = j >> 2, pc = j & 3;
+        const float4 v = *reinterpret_cast<const float4*>(wst + m * 16 + pc * 4);
         st_async_v4(map_to_rank(smem_u32(dst + m * dld + pc * 4), (uint32_t)peer),
                     __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w), map_to_rank(bar, (uint32_t)peer));
     }
 }
-// dst (bf16, row stride dld) of every peer <- bf16(stage[m][0..ncols)), ncols % 8 == 0
-TTS_D void push_bf16_all(const ClCtx& c, const float* stage, int ld, bf16* dst, int dld, int ncols) {
-    const int ppr = ncols >> 3, per_peer = c.G * ppr;
+// same, as bf16 (16 columns = two 16-byte chunks per row)
+TTS_D void push_tile_bf16(const ClCtx& c, const float* wst, bf16* dst, int dld) {
     const uint32_t bar = gather_bar(c);
-    for (int i = c.tid; i < per_peer * CL_SIZE; i += CL_CONSUMERS) {
-        const int peer = i / per_peer, j = i % per_peer, m = j / ppr, pc = j - m * ppr;
-        const float4 v0 = *reinterpret_cast<const float4*>(stage + m * ld + pc * 8);
-        const float4 v1 = *reinterpret_cast<const float4*>(stage + m * ld + pc * 8 + 4);
+    const int per_peer = c.G * 2;
+    for (int i = c.lane; i < per_peer * CL_SIZE; i += 32) {
+        const int peer = i / per_peer, j = i - peer * per_peer, m = j >> 1, pc = j & 1;
+        const float4 v0 = *reinterpret_cast<const float4*>(wst + m * 16 + pc * 8);
+        const float4 v1 = *reinterpret_cast<const float4*>(wst + m * 16 + pc * 8 + 4);
         st_async_v4(map_to_rank(smem_u32(dst + m * dld + pc * 8), (uint32_t)peer),
                     pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w), map_to_rank(bar, (uint32_t)peer));
     }
@@ -367,7 +369,7 @@ TTS_D void push_bf16_all(const ClCtx& c, const float* stage, int ld, bf16* dst, 
 
 // LayerNorm of the gathered rows: ybuf -> xres (f32) + xa (bf16); warp m < G owns row m.  The affine parameters
 // (global memory) are fetched asynchronously into shared memory by ln_prefetch() BEFORE the exchange the rows are
-// waited on (buffer: the upper half of the K-split scratch, idle between GEMMs).
+// waited on; the caller's gather_sync() orders both (cp.async.wait_group precedes its barrier).
 TTS_D void ln_prefetch(const ClCtx& c, const float* g, const float* b) {
     float* dst = reinterpret_cast<float*>(c.smem + SM_RED + 4096);        // [0,512) gamma, [512,1024) beta
     if (c.tid < 256) {
@@ -377,8 +379,6 @@ TTS_D void ln_prefetch(const ClCtx& c, const float* g, const float* b) {
     cp_async_commit();
 }
 TTS_D void cl_layernorm(ClCtx& c, float ln_eps) {
-    cp_async_wait<0>();
-    consumer_bar();
     if (c.warp < c.G) {
         const float* y = reinterpret_cast<const float*>(c.smem + SM_YBUF) + c.warp * 512;
         const float* gb = reinterpret_cast<const float*>(c.smem + SM_RED + 4096);
@@ -411,77 +411,79 @@ TTS_D void cl_layernorm(ClCtx& c, float ln_eps) {
     consumer_bar();
 }
 
-// Attention of this CTA's pairs (utterance w of the group, head = rank): warp w < G owns pair w and runs a
-// flash-style online softmax over 16-row chunks on the tensor cores:
-//   scores[16 rows] = K_chunk[16 x 64] . q        4 x mma.m16n8k16 (A = K rows, B = q in column 0)
-//   out[64 d]      += V_chunk^T[64 x 16] . p      4 x mma.m16n8k16 (A = V^T block, B = p in column 0)
-// self: rows 0..t-1 from the cache chunks + the newest row (k_t, v_t) from qkvbuf; cross: rows 0..len-1.
-// Output rows are staged in `stage` [8][64] and pushed to abuf[m][rank*64 ..] of every CTA.
-TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, float* stage) {
+// Attention of this CTA's pairs (utterance gi of the group, head = rank).  Warps 3 gi .. 3 gi + 2 own pair gi; the cache rows
+// are cut into 16-row sub-chunks and sub-chunk c belongs to warp c % 3 of the pair -- a partition that depends on nothing but
+// the row index, so an utterance's result is bit-identical whatever the group geometry.  Per sub-chunk, on the tensor cores:
+//   scores[16 rows] = K_chunk[16 x 64] . q        4 x mma.m16n8k16 (A = K rows, B = q in every column)
+//   out[64 d]      += V_chunk^T[64 x 16] . p      4 x mma.m16n8k16 (A = V^T sub-block, B = p in every column)
+// with an online softmax per warp.  self: cache rows 0..t-1 plus the newest row (k_t, v_t) from qkvbuf; cross: rows 0..len-1.
+// The pair's first warp merges the three partials (+ the newest row) in fixed order and pushes the pair's 64 outputs as bf16
+// into abuf[gi][rank*64 ..] of every CTA.
+TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, const volatile int* glens) {
     const float* qkv = reinterpret_cast<const float*>(c.smem + SM_QKV);
-    float* pscr = reinterpret_cast<float*>(c.smem + SM_AMERGE) + c.warp * 68;      // 16 probabilities of the current chunk
+    float* part = reinterpret_cast<float*>(c.smem + SM_AMERGE) + c.warp * 68;
     const int g = c.lane >> 2, t4 = c.lane & 3;
     const float qs = 0.125f * kLog2e;
     const int L = self ? t : p.S;
-    const int nck = (L + CL_KV_ROWS - 1) / CL_KV_ROWS;
-    const int gi = c.warp >> 1, par2 = c.warp & 1;         // warps 2p, 2p+1 share pair p: even / odd chunks
+    const int nj = (L + KV_STAGE_ROWS - 1) / KV_STAGE_ROWS;
+    const int gi = c.warp / ATT_WPP, wv = c.warp - gi * ATT_WPP;
     const bool active = gi < c.G;
-    int vlen = L;
-    uint32_t qb0[4] = {0, 0, 0, 0}, qb1[4] = {0, 0, 0, 0};
+    const int vlen = active ? (self ? t : min(L, glens[gi])) : 0;
+    const int nsub = (vlen + 15) >> 4;
     if (active) {
-        if (!self) vlen = min(L, __ldg(p.plens + c.b0 + gi));
+        float m = -INFINITY, l = 0.f, o[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
         // B fragments of q, replicated in all 8 columns (every lane then holds valid scores: the row max needs only
         // 3 shuffles); k slots <-> dims 16 t4 + 4 ks + {0..3}
+        uint32_t qb0[4], qb1[4];
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const float* qp = qkv + gi * 192 + 16 * t4 + 4 * ks;
             qb0[ks] = pack_bf16x2(qp[0] * qs, qp[1] * qs);
             qb1[ks] = pack_bf16x2(qp[2] * qs, qp[3] * qs);
         }
-    }
-    float m = -INFINITY, l = 0.f, o[4][4];
+        float* pscr = part;                              // 16 probabilities of the current sub-chunk (the partial is written afterwards)
+        for (int j = 0; j < nj; ++j) {
+            const uint32_t idx = c.consumed + (uint32_t)(j * c.G + gi);
+            const unsigned char* st = cl_acquire(c, idx);
+            for (int c8 = 0; c8 < 8; ++c8) {
+                const int sc_i = j * 8 + c8;
+                if (sc_i >= nsub) break;                 // warp-uniform
+                if (sc_i % ATT_WPP != wv) continue;
+                const unsigned char* kb = st + (c8 >> 2) * 16384 + (c8 & 3) * 2048;
+                const unsigned char* vb = kb + 8192;
+                uint32_t kr[8], kr8[8];
+                uint2 vf[4][2];
+                {
+                    const int par = g & 1;               // XOR-ordered 16-byte loads: conflict-free at a 128 B row stride
+                    const uint4 ka = *reinterpret_cast<const uint4*>(kb + g * 128 + ((2 * t4 + par) << 4));
+                    const uint4 kbb = *reinterpret_cast<const uint4*>(kb + g * 128 + ((2 * t4 + 1 - par) << 4));
+                    const uint4 kc = *reinterpret_cast<const uint4*>(kb + (g + 8) * 128 + ((2 * t4 + par) << 4));
+                    const uint4 kd = *reinterpret_cast<const uint4*>(kb + (g + 8) * 128 + ((2 * t4 + 1 - par) << 4));
+                    const uint4 lo0 = par ? kbb : ka, hi0 = par ? ka : kbb, lo8 = par ? kd : kc, hi8 = par ? kc : kd;
+                    kr[0] = lo0.x; kr[1] = lo0.y; kr[2] = lo0.z; kr[3] = lo0.w; kr[4] = hi0.x; kr[5] = hi0.y; kr[6] = hi0.z; kr[7] = hi0.w;
+                    kr8[0] = lo8.x; kr8[1] = lo8.y; kr8[2] = lo8.z; kr8[3] = lo8.w; kr8[4] = hi8.x; kr8[5] = hi8.y; kr8[6] = hi8.z; kr8[7] = hi8.w;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-    for (int ci = 0; ci < nck; ++ci) {
-        const bool mine = active && (ci & 1) == par2;
-        if (!mine) { ++c.consumed; continue; }           // not my chunk: the producer / its owner release it
-        const unsigned char* st = cl_acquire(c);
-        uint32_t kr[8], kr8[8];
-        uint2 vf[4][2];
-        {
-            const unsigned char* kb = st + gi * 2048;
-            const unsigned char* vb = st + 16384 + gi * 2048;
-            const int par = g & 1;                       // XOR-ordered 16-byte loads: conflict-free at a 128 B row stride
-            const uint4 ka = *reinterpret_cast<const uint4*>(kb + g * 128 + ((2 * t4 + par) << 4));
-            const uint4 kbb = *reinterpret_cast<const uint4*>(kb + g * 128 + ((2 * t4 + 1 - par) << 4));
-            const uint4 kc = *reinterpret_cast<const uint4*>(kb + (g + 8) * 128 + ((2 * t4 + par) << 4));
-            const uint4 kd = *reinterpret_cast<const uint4*>(kb + (g + 8) * 128 + ((2 * t4 + 1 - par) << 4));
-            const uint4 lo0 = par ? kbb : ka, hi0 = par ? ka : kbb, lo8 = par ? kd : kc, hi8 = par ? kc : kd;
-            kr[0] = lo0.x; kr[1] = lo0.y; kr[2] = lo0.z; kr[3] = lo0.w; kr[4] = hi0.x; kr[5] = hi0.y; kr[6] = hi0.z; kr[7] = hi0.w;
-            kr8[0] = lo8.x; kr8[1] = lo8.y; kr8[2] = lo8.z; kr8[3] = lo8.w; kr8[4] = hi8.x; kr8[5] = hi8.y; kr8[6] = hi8.z; kr8[7] = hi8.w;
+                    for (int dt = 0; dt < 4; ++dt) {     // V^T sub-block [64 d][16 rows]: rows 4 t4 .. 4 t4 + 3 of d = 16 dt + g (+8)
+                        vf[dt][0] = *reinterpret_cast<const uint2*>(vb + (dt * 16 + g) * 32 + 8 * t4);
+                        vf[dt][1] = *reinterpret_cast<const uint2*>(vb + (dt * 16 + g + 8) * 32 + 8 * t4);
+                    }
+                }
+                float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int dt = 0; dt < 4; ++dt) {             // V^T block [64 d][16 rows]: rows 4 t4 .. 4 t4 + 3 of d = 16 dt + g (+8)
-                vf[dt][0] = *reinterpret_cast<const uint2*>(vb + (dt * 16 + g) * 32 + 8 * t4);
-                vf[dt][1] = *reinterpret_cast<const uint2*>(vb + (dt * 16 + g + 8) * 32 + 8 * t4);
-            }
-        }
-        cl_release(c);
-        {
-            float sc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t a[4] = {kr[2 * ks], kr8[2 * ks], kr[2 * ks + 1], kr8[2 * ks + 1]};
-                mma_bf16_16816(sc, a, qb0[ks], qb1[ks]);
-            }
-            const int r0 = ci * CL_KV_ROWS + g;
-            const float s0 = r0 < vlen ? sc[0] : -INFINITY;
-            const float s8 = r0 + 8 < vlen ? sc[2] : -INFINITY;
-            float mx = fmaxf(s0, s8);                    // all columns are equal: reduce over the 8 row-groups only
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-            const float mnew = fmaxf(m, mx);
-            if (mnew > -INFINITY) {                      // warp-uniform
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t a[4] = {kr[2 * ks], kr8[2 * ks], kr[2 * ks + 1], kr8[2 * ks + 1]};
+                    mma_bf16_16816(sc, a, qb0[ks], qb1[ks]);
+                }
+                const int r0 = sc_i * 16 + g;
+                const float s0 = r0 < vlen ? sc[0] : -INFINITY;
+                const float s8 = r0 + 8 < vlen ? sc[2] : -INFINITY;
+                float mx = fmaxf(s0, s8);                // all columns are equal: reduce over the 8 row-groups only
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+                const float mnew = fmaxf(m, mx);         // finite: the sub-chunk holds at least one valid row
                 const float p0 = fast_exp2(s0 - mnew), p8 = fast_exp2(s8 - mnew);
                 if (t4 == 0) { pscr[g] = p0; pscr[g + 8] = p8; }
                 if (mnew != m) {                         // warp-uniform: rescale only when the running max moved
@@ -502,47 +504,59 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, floa
                 }
                 m = mnew;
             }
+            cl_release(c, idx);
         }
-    }
-    if (active) {
-        if (self && par2 == 0) {                         // newest row: bf16-rounded q, k_t, v_t exactly as the MMA path sees them
-            const float* qp = qkv + gi * 192 + 2 * c.lane;
-            const float2 qd = unpack_bf16x2(pack_bf16x2(qp[0] * qs, qp[1] * qs));
-            const float2 kd = unpack_bf16x2(pack_bf16x2(qp[64], qp[65]));
-            const float st = warp_sum(qd.x * kd.x + qd.y * kd.y);
-            const float mnew = fmaxf(m, st);
-            const float scale = (m == -INFINITY) ? 0.f : fast_exp2(m - mnew), pt = fast_exp2(st - mnew);
-            l = l * scale + (c.lane == 0 ? pt : 0.f);
-#pragma unroll
-            for (int dt = 0; dt < 4; ++dt) {
-                const float v0 = __bfloat162float(__float2bfloat16(qkv[gi * 192 + 128 + dt * 16 + g]));
-                const float v8 = __bfloat162float(__float2bfloat16(qkv[gi * 192 + 128 + dt * 16 + g + 8]));
-                o[dt][0] = o[dt][0] * scale + pt * v0;
-                o[dt][2] = o[dt][2] * scale + pt * v8;
-            }
-            m = mnew;
-        }
-        // partial (m, l, o[64]) of this warp -> scratch; the even warp of the pair merges the two halves
+        // partial (m, l, o[64]) of this warp -> scratch
         const float ls = warp_sum(l);
         if (t4 == 0) {
 #pragma unroll
-            for (int dt = 0; dt < 4; ++dt) { pscr[dt * 16 + g] = o[dt][0]; pscr[dt * 16 + g + 8] = o[dt][2]; }
+            for (int dt = 0; dt < 4; ++dt) { part[dt * 16 + g] = o[dt][0]; part[dt * 16 + g + 8] = o[dt][2]; }
         }
-        if (c.lane == 0) { pscr[64] = m; pscr[65] = ls; }
+        if (c.lane == 0) { part[64] = m; part[65] = ls; }
     }
+    c.consumed += (uint32_t)(nj * c.G);
     consumer_bar();
-    if (active && par2 == 0) {
-        const float* pa = pscr;
-        const float* pb = pscr + 68;
-        const float ma = pa[64], mb = pb[64], mm = fmaxf(ma, mb);
-        const float ea = (ma == -INFINITY) ? 0.f : fast_exp2(ma - mm), eb = (mb == -INFINITY) ? 0.f : fast_exp2(mb - mm);
-        const float ls = pa[65] * ea + pb[65] * eb;
-        const float inv = ls > 0.f ? 1.f / ls : 0.f;
-        stage[gi * 64 + c.lane] = (pa[c.lane] * ea + pb[c.lane] * eb) * inv;
-        stage[gi * 64 + 32 + c.lane] = (pa[32 + c.lane] * ea + pb[32 + c.lane] * eb) * inv;
+    if (active && wv == 0) {                             // merge the pair's three partials (+ the newest row) in fixed order
+        const float* pa = part;
+        float mm = fmaxf(fmaxf(pa[64], pa[68 + 64]), pa[136 + 64]);
+        float st_new = -INFINITY;
+        if (self) {                                      // newest row: bf16-rounded q, k_t, v_t exactly as the MMA path would see them
+            const float* qp = qkv + gi * 192 + 2 * c.lane;
+            const float2 qd = unpack_bf16x2(pack_bf16x2(qp[0] * qs, qp[1] * qs));
+            const float2 kd = unpack_bf16x2(pack_bf16x2(qp[64], qp[65]));
+            st_new = warp_sum(qd.x * kd.x + qd.y * kd.y);
+            mm = fmaxf(mm, st_new);
+        }
+        float lsum = 0.f, v0 = 0.f, v1 = 0.f;
+        if (mm > -INFINITY) {
+#pragma unroll
+            for (int q = 0; q < ATT_WPP; ++q) {
+                const float mq = pa[q * 68 + 64];
+                const float e = (mq == -INFINITY) ? 0.f : fast_exp2(mq - mm);
+                lsum += pa[q * 68 + 65] * e;
+                v0 += pa[q * 68 + c.lane] * e; v1 += pa[q * 68 + 32 + c.lane] * e;
+            }
+            if (self) {
+                const float pt = fast_exp2(st_new - mm);
+                lsum += pt;
+                v0 += pt * __bfloat162float(__float2bfloat16(qkv[gi * 192 + 128 + c.lane]));
+                v1 += pt * __bfloat162float(__float2bfloat16(qkv[gi * 192 + 128 + 32 + c.lane]));
+            }
+        }
+        const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+        float* ost = reinterpret_cast<float*>(c.smem + SM_RED) + gi * 64;
+        ost[c.lane] = v0 * inv; ost[32 + c.lane] = v1 * inv;
+        __syncwarp();
+        bf16* dst = reinterpret_cast<bf16*>(c.smem + SM_ABUF) + gi * LDX512 + c.rank * 64;
+        const uint32_t bar = gather_bar(c);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {                    // 8 peers x 8 chunks of 8 bf16
+            const int i = c.lane + 32 * k, peer = i >> 3, ch = i & 7;
+            const float4 a = *reinterpret_cast<const float4*>(ost + ch * 8), b = *reinterpret_cast<const float4*>(ost + ch * 8 + 4);
+            st_async_v4(map_to_rank(smem_u32(dst + ch * 8), (uint32_t)peer), pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w),
+                        pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w), map_to_rank(bar, (uint32_t)peer));
+        }
     }
-    consumer_bar();
-    push_bf16_all(c, stage, 64, reinterpret_cast<bf16*>(c.smem + SM_ABUF) + c.rank * 64, LDX512, 64);
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -551,12 +565,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
     ClCtx c;
     c.smem = cl_smem;
     c.full = reinterpret_cast<uint64_t*>(cl_smem + SM_MISC);
-    c.empty = c.full + CL_STAGES;
+    c.empty = c.full + CL_FULL_BARS;
     c.gsync = c.empty + CL_STAGES;
     // flags[0] finished utterances of the group (rank 5 counts), [1] consumers done (producer stop), [2] final consumed count
-    // hrec: one 16-byte record per rank, pushed in the head phase (rank 5: finished count)
-    volatile int* flags = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 128);
-    volatile int* hrec = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 128 + 32);     // [8 ranks][4]
+    // hrec: one 16-byte record per rank, pushed in the head phase (rank 5: finished count); glens: phoneme lengths of the group
+    volatile int* flags = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 192);
+    volatile int* hrec = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 192 + 32);             // [8 ranks][4]
+    volatile int* glens = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 192 + 32 + 128);      // [CL_G]
     c.rank = (int)cluster_ctarank();
     c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
     const int cid = (int)cluster_id_x(), ncl = (int)cluster_nid_x();
@@ -572,7 +587,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
     bf16* h1 = reinterpret_cast<bf16*>(cl_smem + SM_H1);
     bf16* h2 = reinterpret_cast<bf16*>(cl_smem + SM_H2);
     bf16* fbuf = reinterpret_cast<bf16*>(cl_smem + SM_FBUF);
-    float* stg = recv;                                   // epilogue staging (free outside the FFN2 exchange)
+    float* wst = recv + (c.warp & 15) * (CL_G * 16);     // this warp's private epilogue tile [G][16] (recv is free outside the FFN2 exchange)
     const bool stamper = p.ts != nullptr && cid == 0 && c.rank == 0 && c.tid == 0;
     auto stamp = [&](int t, int idx) {
         if (stamper) {
@@ -582,19 +597,31 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
         }
     };
 
+    // debug dump: slot `slot` <- rows [0, G) x n values (row stride ld) of a shared-memory buffer, widened to fp32
+    const bool dumper = p.dbg != nullptr && cid == 0 && c.rank == p.dbg_rank && !is_producer;
+    auto dbg_dump = [&](int t, int slot, const void* src, int ld, int n, bool is_bf16) {
+        if (dumper && t == t0) {
+            for (int i = c.tid; i < c.G * n; i += CL_CONSUMERS) {
+                const int m = i / n, k = i - m * n;
+                p.dbg[(size_t)slot * 2560 + i] = is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(src)[m * ld + k]) : reinterpret_cast<const float*>(src)[m * ld + k];
+            }
+        }
+    };
+
     for (int grp = cid; grp < p.ngroups; grp += ncl) {
         c.b0 = grp * p.G; c.G = min(p.G, p.B - c.b0);
         // ---- (re)initialise the ring and the activation buffers
         if (!is_producer)
             for (int i = c.tid; i < (SM_MISC - SM_XRES) / 4; i += CL_CONSUMERS) reinterpret_cast<uint32_t*>(cl_smem + SM_XRES)[i] = 0u;
         if (c.tid == 0) {
-            for (int s = 0; s < CL_STAGES; ++s) { mbar_init(&c.full[s], 1); mbar_init(&c.empty[s], CL_WARPS); }
+            for (int s = 0; s < CL_FULL_BARS; ++s) mbar_init(&c.full[s], 1);
+            for (int s = 0; s < CL_STAGES; ++s) mbar_init(&c.empty[s], CL_WARPS);
             mbar_init(&c.gsync[0], 1); mbar_init(&c.gsync[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             mbar_expect_tx(&c.gsync[0], gather_bytes(0, c.G));          // phases 0 and 1 are armed before the start barrier
             mbar_expect_tx(&c.gsync[1], gather_bytes(1, c.G));
             int nf = 0;
-            for (int m = 0; m < c.G; ++m) nf += p.finished[c.b0 + m];
+            for (int m = 0; m < c.G; ++m) { nf += p.finished[c.b0 + m]; glens[m] = p.plens[c.b0 + m]; }
             flags[0] = nf; flags[1] = 0; flags[2] = 0;
         }
         __syncthreads();
@@ -614,103 +641,110 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
         hw_cluster_sync();
         if (skip) {
         } else if (is_producer) {
-            cl_producer(p, cl_smem, c.full, c.empty, flags, c.rank, c.b0, c.G, t0, t0 + n_steps, c.lane);
+            if (c.lane == 0) cl_producer(p, cl_smem, c.full, c.empty, flags, glens, c.rank, c.b0, c.G, t0, t0 + n_steps);
             __syncwarp();                                // lanes 1..31 park here: the cluster barrier below is .aligned
         } else {
             for (int t = t0; t < t0 + n_steps; ++t) {
                 // ================= decoder prenet (dropout always on, P7) =================
-                cl_gemm(c, 1, 2, 2, false, fbuf, LDX128,
+                cl_gemm<4, 1>(c, 2, fbuf, LDX128,
                         [&](int ti, int n) { return __ldg(p.b_fc1 + c.rank * 32 + ti * 16 + n); },
                         [&](int ti, int n, int m, float v) {
-                            const int cc = ti * 16 + n, col = c.rank * 32 + cc;
+                            const int col = c.rank * 32 + ti * 16 + n;
                             v = fmaxf(v, 0.f);
-                            stg[m * 32 + cc] = keep_bit(p.seed, SITE_DEC_PRENET_FC1, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
+                            wst[m * 16 + n] = keep_bit(p.seed, SITE_DEC_PRENET_FC1, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
                         });
-                push_bf16_all(c, stg, 32, h1 + c.rank * 32, LDX256, 32);
-                gather_wait(c);
+                if (c.warp < 2) { __syncwarp(); push_tile_bf16(c, wst, h1 + c.rank * 32 + c.warp * 16, LDX256); }
+                gather_sync(c);
                 stamp(t, 0);
-                cl_gemm(c, 1, 2, 4, false, h1, LDX256,
+                cl_gemm<8, 1>(c, 2, h1, LDX256,
                         [&](int ti, int n) { return __ldg(p.b_fc2 + c.rank * 32 + ti * 16 + n); },
                         [&](int ti, int n, int m, float v) {
-                            const int cc = ti * 16 + n, col = c.rank * 32 + cc;
+                            const int col = c.rank * 32 + ti * 16 + n;
                             v = fmaxf(v, 0.f);
-                            stg[m * 32 + cc] = keep_bit(p.seed, SITE_DEC_PRENET_FC2, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
+                            wst[m * 16 + n] = keep_bit(p.seed, SITE_DEC_PRENET_FC2, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
                         });
-                push_bf16_all(c, stg, 32, h2 + c.rank * 32, LDX256, 32);
-                gather_wait(c);
+                if (c.warp < 2) { __syncwarp(); push_tile_bf16(c, wst, h2 + c.rank * 32 + c.warp * 16, LDX256); }
+                gather_sync(c);
                 stamp(t, 1);
-                cl_gemm(c, 1, 4, 4, false, h2, LDX256,
+                cl_gemm<8, 1>(c, 4, h2, LDX256,
                         [&](int ti, int n) {
                             const int col = c.rank * CL_NS + ti * 16 + n;
                             return __ldg(p.b_proj + col) + p.dec_alpha * __ldg(p.pe + (size_t)t * kDModel + col);
                         },
-                        [&](int ti, int n, int m, float v) { stg[m * CL_NS + ti * 16 + n] = v; });
-                push_f32_all(c, stg, CL_NS, xres + c.rank * CL_NS, 512, CL_NS);
-                push_bf16_all(c, stg, CL_NS, xa + c.rank * CL_NS, LDX512, CL_NS);
-                gather_wait(c);
+                        [&](int, int n, int m, float v) { wst[m * 16 + n] = v; });
+                if (c.warp < 4) {
+                    __syncwarp();
+                    push_tile_f32(c, wst, xres + c.rank * CL_NS + c.warp * 16, 512);
+                    push_tile_bf16(c, wst, xa + c.rank * CL_NS + c.warp * 16, LDX512);
+                }
+                gather_sync(c);
                 stamp(t, 2);
+                dbg_dump(t, 0, xa, LDX512, 512, true);
 
                 for (int l = 0; l < 6; ++l) {
                     const ClusterLayerParams& W = p.layer[l];
                     // ---- q, k, v of head `rank` for every row of the group (local; k_t, v_t appended to the cache)
-                    cl_gemm(c, 8, 12, 1, false, xa, LDX512,
+                    cl_gemm<16, 1>(c, 12, xa, LDX512,
                             [&](int ti, int n) { const int cc = ti * 16 + n; return __ldg(W.bqkv + (cc >> 6) * 512 + c.rank * 64 + (cc & 63)); },
                             [&](int ti, int n, int m, float v) {
                                 const int cc = ti * 16 + n, part = cc >> 6, dd = cc & 63;
                                 qkvb[m * 192 + cc] = v;
-                                if (part > 0) {               // append to the cache: K row-major, V in transposed 16-row blocks
-                                    const size_t pbase = (((size_t)(l * 2 + part - 1) * p.B + c.b0 + m) * kHeads + c.rank) * p.Tpad * kDHead;
-                                    const size_t off = part == 1 ? (size_t)t * kDHead + dd : (size_t)(t >> 4) * 1024 + dd * 16 + (t & 15);
-                                    p.self_kv[pbase + off] = __float2bfloat16(v);
+                                if (part > 0) {               // append row t to the cache block t / 64
+                                    bf16* blk = p.self_kv + kv_block_offset(l, p.B, c.b0 + m, c.rank, p.nblk_self, t >> 6);
+                                    blk[part == 1 ? kv_k_elem(t & 63, dd) : kv_v_elem(t & 63, dd)] = __float2bfloat16(v);
                                 }
                             });
-                    // the appended rows are read by the async proxy (TMA copies) from the next step on: order the
-                    // generic-proxy stores before them here, on the writer side (a fence next to every copy would
-                    // serialise the producer's copies); the ring's empty/full mbarriers carry the rest of the ordering
-                    asm volatile("fence.proxy.async;" ::: "memory");
+                    consumer_bar();
                     stamp(t, 3 + 8 * l);
-                    cl_attention(p, c, true, t, stg);
-                    gather_wait(c);
+                    if (l == 0) dbg_dump(t, 1, qkvb, 192, 192, false);
+                    cl_attention(p, c, true, t, glens);
+                    gather_sync(c);
                     stamp(t, 4 + 8 * l);
+                    if (l == 0) dbg_dump(t, 2, abuf, LDX512, 512, true);
                     // ---- O projection + residual, gathered -> LayerNorm 1
-                    cl_gemm(c, 2, 4, 4, false, abuf, LDX512,
-                            [&](int ti, int n) { return __ldg(W.bo + c.rank * CL_NS + ti * 16 + n); },
-                            [&](int ti, int n, int m, float v) {
-                                const int cc = ti * 16 + n;
-                                stg[m * CL_NS + cc] = v + xres[m * 512 + c.rank * CL_NS + cc];
-                            });
                     ln_prefetch(c, W.ln1g, W.ln1b);
-                    push_f32_all(c, stg, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
-                    gather_wait(c);
+                    cl_gemm<16, 1>(c, 4, abuf, LDX512,
+                            [&](int ti, int n) { return __ldg(W.bo + c.rank * CL_NS + ti * 16 + n); },
+                            [&](int ti, int n, int m, float v) { wst[m * 16 + n] = v + xres[m * 512 + c.rank * CL_NS + ti * 16 + n]; });
+                    if (c.warp < 4) { __syncwarp(); push_tile_f32(c, wst, ybuf + c.rank * CL_NS + c.warp * 16, 512); }
+                    cp_async_wait<0>();
+                    gather_sync(c);
                     cl_layernorm(c, p.ln_eps);
                     stamp(t, 5 + 8 * l);
+                    if (l == 0) dbg_dump(t, 3, xa, LDX512, 512, true);
                     // ---- cross-attention query of head `rank` (local)
-                    cl_gemm(c, 2, 4, 4, false, xa, LDX512,
+                    cl_gemm<16, 1>(c, 4, xa, LDX512,
                             [&](int ti, int n) { return __ldg(W.bq2 + c.rank * CL_NS + ti * 16 + n); },
                             [&](int ti, int n, int m, float v) { qkvb[m * 192 + ti * 16 + n] = v; });
+                    consumer_bar();
                     stamp(t, 6 + 8 * l);
-                    cl_attention(p, c, false, t, stg);
-                    gather_wait(c);
+                    cl_attention(p, c, false, t, glens);
+                    gather_sync(c);
                     stamp(t, 7 + 8 * l);
-                    cl_gemm(c, 2, 4, 4, false, abuf, LDX512,
-                            [&](int ti, int n) { return __ldg(W.bo2 + c.rank * CL_NS + ti * 16 + n); },
-                            [&](int ti, int n, int m, float v) {
-                                const int cc = ti * 16 + n;
-                                stg[m * CL_NS + cc] = v + xres[m * 512 + c.rank * CL_NS + cc];
-                            });
+                    if (l == 0) dbg_dump(t, 4, abuf, LDX512, 512, true);
                     ln_prefetch(c, W.ln2g, W.ln2b);
-                    push_f32_all(c, stg, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
-                    gather_wait(c);
+                    cl_gemm<16, 1>(c, 4, abuf, LDX512,
+                            [&](int ti, int n) { return __ldg(W.bo2 + c.rank * CL_NS + ti * 16 + n); },
+                            [&](int ti, int n, int m, float v) { wst[m * 16 + n] = v + xres[m * 512 + c.rank * CL_NS + ti * 16 + n]; });
+                    if (c.warp < 4) { __syncwarp(); push_tile_f32(c, wst, ybuf + c.rank * CL_NS + c.warp * 16, 512); }
+                    cp_async_wait<0>();
+                    gather_sync(c);
                     cl_layernorm(c, p.ln_eps);
                     stamp(t, 8 + 8 * l);
+                    if (l == 0) dbg_dump(t, 5, xa, LDX512, 512, true);
                     // ---- FFN: hidden slice [256 rank, +256) stays local (bf16); FFN2 is split along K
-                    cl_gemm(c, 8, 16, 1, false, xa, LDX512,
+                    cl_gemm<16, 1>(c, 16, xa, LDX512,
                             [&](int ti, int n) { return __ldg(W.b1 + c.rank * 256 + ti * 16 + n); },
                             [&](int ti, int n, int m, float v) { hbuf[m * LDX256 + ti * 16 + n] = __float2bfloat16(fmaxf(v, 0.f)); });
+                    consumer_bar();
                     stamp(t, 9 + 8 * l);
+                    if (l == 0) dbg_dump(t, 6, hbuf, LDX256, 256, true);
                     // partial sums over this rank's 256 hidden units, staged in ybuf (free between LN2 and the y3 gather)
-                    cl_gemm(c, 8, 32, 1, true, hbuf, LDX256, [&](int, int) { return 0.f; },
+                    ln_prefetch(c, W.ln3g, W.ln3b);
+                    cl_gemm<8, 2>(c, 16, hbuf, LDX256, [&](int, int) { return 0.f; },
                             [&](int ti, int n, int m, float v) { ybuf[m * 512 + ti * 16 + n] = v; });
+                    consumer_bar();
+                    if (l == 0) dbg_dump(t, 8, ybuf, 512, 512, false);
                     {
                         const uint32_t bar = gather_bar(c);
                         for (int i = c.tid; i < CL_SIZE * c.G * 16; i += CL_CONSUMERS) {   // reduce-scatter: 64 columns to each peer
@@ -721,28 +755,38 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                                         map_to_rank(bar, (uint32_t)peer));
                         }
                     }
-                    const float b2v = __ldg(W.b2 + c.rank * CL_NS + (c.tid & 63));
-                    ln_prefetch(c, W.ln3g, W.ln3b);
-                    gather_wait(c);
-                    {
-                        float* st2 = reinterpret_cast<float*>(c.smem + SM_RED);    // [8][64] staging of my reduced columns
-                        const int m = c.tid >> 6, cc = c.tid & 63, col = c.rank * CL_NS + cc;
-                        if (m < c.G) {
-                            float v = b2v + xres[m * 512 + col];
+                    gather_sync(c);
+                    if (l == 0) dbg_dump(t, 10, recv, 2560, 2560, false);
+                    if (c.tid < c.G * 16) {              // my 64 columns: 8 partials (fixed order) + bias + residual -> every peer's ybuf
+                        const int m = c.tid >> 4, pc = c.tid & 15, col = c.rank * CL_NS + pc * 4;
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(W.b2 + col));
+                        const float4 xr = *reinterpret_cast<const float4*>(xres + m * 512 + col);
+                        float4 v = make_float4(bb.x + xr.x, bb.y + xr.y, bb.z + xr.z, bb.w + xr.w);
 #pragma unroll
-                            for (int r = 0; r < CL_SIZE; ++r) v += recv[(r * CL_G + m) * CL_NS + cc];    // fixed order
-                            st2[m * CL_NS + cc] = v;
+                        for (int r = 0; r < CL_SIZE; ++r) {
+                            const float4 q = *reinterpret_cast<const float4*>(recv + (r * CL_G + m) * CL_NS + pc * 4);
+                            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
                         }
-                        consumer_bar();
-                        push_f32_all(c, st2, CL_NS, ybuf + c.rank * CL_NS, 512, CL_NS);
+                        const uint32_t bar = gather_bar(c);
+#pragma unroll
+                        for (int peer = 0; peer < CL_SIZE; ++peer)
+                            st_async_v4(map_to_rank(smem_u32(ybuf + m * 512 + col), (uint32_t)peer), __float_as_uint(v.x), __float_as_uint(v.y),
+                                        __float_as_uint(v.z), __float_as_uint(v.w), map_to_rank(bar, (uint32_t)peer));
                     }
-                    gather_wait(c);
+                    cp_async_wait<0>();
+                    gather_sync(c);
+                    if (l == 0) dbg_dump(t, 9, ybuf, 512, 512, false);
                     cl_layernorm(c, p.ln_eps);
                     stamp(t, 10 + 8 * l);
+                    if (l == 0) dbg_dump(t, 7, xa, LDX512, 512, true);
                 }
+                // The cache rows appended in this step are read by the async proxy (bulk copies) from the next step on: order the
+                // generic-proxy stores before them here, once per step and long after the stores were issued (a fence next to every
+                // append would wait for the stores of that very moment).
+                asm volatile("fence.proxy.async;" ::: "memory");
                 // ================= [mel | stop] heads: ranks 0..5 own 16 of the 81(+15) columns =================
                 if (c.rank < 6) {
-                    cl_gemm(c, 1, 1, 8, false, xa, LDX512,
+                    cl_gemm<16, 1>(c, 1, xa, LDX512,
                             [&](int, int n) { const int col = c.rank * 16 + n; return col <= 80 ? __ldg(p.b_head + col) : 0.f; },
                             [&](int, int n, int m, float v) {
                                 const int col = c.rank * 16 + n, b = c.b0 + m;
@@ -754,16 +798,19 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                                         atomicAdd(const_cast<int*>(flags), 1);                   // rank 5 keeps the group's count
                                     }
                                 }
-                                stg[m * 16 + n] = v;
+                                wst[m * 16 + n] = v;
                             });
-                    if (c.rank < 5) push_bf16_all(c, stg, 16, fbuf + c.rank * 16, LDX128, 16);   // the frame = next step's prenet input
                 }
-                if (c.tid < CL_SIZE) {                    // every rank contributes one record (rank 5: finished count) to every peer
-                    const uint32_t bar = gather_bar(c);
-                    st_async_v4(map_to_rank(smem_u32(const_cast<int*>(hrec) + c.rank * 4), (uint32_t)c.tid),
-                                (uint32_t)flags[0], 0u, 0u, 0u, map_to_rank(bar, (uint32_t)c.tid));
+                if (c.warp == 0) {
+                    __syncwarp();
+                    if (c.rank < 5) push_tile_bf16(c, wst, fbuf + c.rank * 16, LDX128);           // the frame = next step's prenet input
+                    if (c.lane < CL_SIZE) {              // every rank contributes one record (rank 5: finished count) to every peer
+                        const uint32_t bar = gather_bar(c);
+                        st_async_v4(map_to_rank(smem_u32(const_cast<int*>(hrec) + c.rank * 4), (uint32_t)c.lane),
+                                    (uint32_t)flags[0], 0u, 0u, 0u, map_to_rank(bar, (uint32_t)c.lane));
+                    }
                 }
-                gather_wait(c);
+                gather_sync(c);
                 stamp(t, 51);
                 if (hrec[5 * 4] >= c.G) break;                               // every utterance of the group has fired
             }

@@ -31,10 +31,10 @@ struct GemmParams {
     int dropw_site; uint32_t dropw_thresh; float dropw_scale;   // word dropout (training, P12) of (acc + bias + alpha * pe), BEFORE the residual
     float* out_f32; bf16* out_bf16; int ldo;
     int scatter;                     // GemmScatter
-    // SC_CROSS_KV: out_bf16 = cache [layers][2][B][H][S][64], N = layers * 1024, T = S
+    // SC_CROSS_KV: out_bf16 = cache [layers][2][B][H][Lpad][64], N = layers * 1024, T = S; SC_CROSS_KV_VT: the decode kernel's blocks
     // SC_HEAD    : out_f32 = mel_before [M][80], out2_f32 = stop_logits [M]
     float* out2_f32; int B;
-    int Lpad;                        // SC_CROSS_KV*: row capacity of the cache per (layer, kv, b, h), multiple of 16
+    int Lpad;                        // SC_CROSS_KV*: row capacity of the cache per (layer, b, h): multiple of 16 (row-major) / 64 (blocks)
 };
 
 TTS_D void gemm_store(const GemmParams& p, int m, int n, float v0, float v1) {
@@ -71,18 +71,24 @@ TTS_D void gemm_store(const GemmParams& p, int m, int n, float v0, float v1) {
         if (has1) v1 = keep_bit(seed, p.drop_site, t, p.utt_offset + b, n + 1) ? 2.f * v1 : 0.f;
     }
     if (p.lens && t >= p.lens[b]) { v0 = 0.f; v1 = 0.f; }
-    if (p.scatter == SC_CROSS_KV || p.scatter == SC_CROSS_KV_VT) {
-        // n = layer * 1024 + kv * 512 + h * 64 + d  ->  cache [layer][kv][B][H][Lpad * 64]; K rows are row-major, V is
-        // row-major too (SC_CROSS_KV, teacher-forced flash attention) or in transposed 16-row blocks
-        // [Lpad/16][64 d][16 rows] (SC_CROSS_KV_VT, decode_cluster.cuh)
+    if (p.scatter == SC_CROSS_KV) {
+        // teacher-forced flash attention: n = layer * 1024 + kv * 512 + h * 64 + d  ->  cache [layer][kv][B][H][Lpad][64], row-major
         const int lkv = n >> 9, h = (n >> 6) & 7, d = n & 63;
         const size_t base = (((size_t)lkv * p.B + b) * kHeads + h) * (size_t)p.Lpad * kDHead;
-        if (p.scatter == SC_CROSS_KV_VT && (lkv & 1)) {
-            bf16* blk = p.out_bf16 + base + (size_t)(t >> 4) * 1024 + (t & 15);
-            blk[d * 16] = __float2bfloat16(v0);
-            blk[(d + 1) * 16] = __float2bfloat16(v1);
+        *reinterpret_cast<uint32_t*>(p.out_bf16 + base + (size_t)t * kDHead + d) = pack_bf16x2(v0, v1);
+        return;
+    }
+    if (p.scatter == SC_CROSS_KV_VT) {
+        // decode kernel (decode_cluster.cuh): per (layer, b, h) 64-row blocks of 8192 elements,
+        // [K rows row-major [64][64] | V in four transposed 16-row sub-blocks [64 d][16 rows]]; Lpad = 64 * blocks
+        const int layer = n >> 10, kv = (n >> 9) & 1, h = (n >> 6) & 7, d = n & 63, r = t & 63;
+        bf16* blk = p.out_bf16 + ((((size_t)layer * p.B + b) * kHeads + h) * (size_t)(p.Lpad >> 6) + (t >> 6)) * 8192;
+        if (kv) {
+            bf16* q = blk + 4096 + (r >> 4) * 1024 + (r & 15);
+            q[d * 16] = __float2bfloat16(v0);
+            q[(d + 1) * 16] = __float2bfloat16(v1);
         } else {
-            *reinterpret_cast<uint32_t*>(p.out_bf16 + base + (size_t)t * kDHead + d) = pack_bf16x2(v0, v1);
+            *reinterpret_cast<uint32_t*>(blk + r * kDHead + d) = pack_bf16x2(v0, v1);
         }
         return;
     }

@@ -32,7 +32,7 @@ struct TtsHandle {
     std::string err;
     std::map<std::string, std::vector<float>> staged;
     bool finalized = false;
-    int decode_timestamps = 0;
+    int decode_timestamps = 0, decode_debug = 0;
     int cluster_group = 0;                                            // utterances per cluster (1..8); 0 = auto
     int cluster_ok = -1, max_clusters = 0;                            // probed lazily
     unsigned char* cl_wpack = nullptr;                                // [16][CLW_RANK_BYTES] (own allocation)
@@ -86,15 +86,21 @@ struct Ws {
     size_t total = 0;
     size_t self_kv, cross_kv, mel_before, stop_logits, lens, finished, scalars, ts;
     size_t x, x2, wide, a, y, mel16, mel32, ph, plens, mlens;         // sequence-parallel activations
-    int Tpad, Spad;
+    int Tpad, Spad, nblk_self, nblk_cross;
+    size_t self_kv_bytes, cross_kv_bytes;
     static Ws make(int B, int S, int T) {
         Ws w; size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
         const size_t P = (size_t)B * kHeads;
         const size_t M = (size_t)B * (size_t)(S > T ? S : T);
         w.Tpad = (T + 15) / 16 * 16; w.Spad = (S + 15) / 16 * 16;
-        w.self_kv = take((size_t)6 * 2 * P * w.Tpad * kDHead * 2);
-        w.cross_kv = take((size_t)6 * 2 * P * w.Spad * kDHead * 2);
+        // K/V caches of the decode kernel: 64-row blocks of 16 KB (K + V interleaved, decode_cluster.cuh).  The teacher-forced
+        // path keeps its cross K/V row-major in the same region ([6][2][B][H][Spad][64], never larger).
+        w.nblk_self = (T + KV_BLOCK_ROWS - 1) / KV_BLOCK_ROWS; w.nblk_cross = (S + KV_BLOCK_ROWS - 1) / KV_BLOCK_ROWS;
+        w.self_kv_bytes = (size_t)6 * P * w.nblk_self * KV_BLOCK_ELEMS * 2;
+        w.cross_kv_bytes = (size_t)6 * P * w.nblk_cross * KV_BLOCK_ELEMS * 2;
+        w.self_kv = take(w.self_kv_bytes);
+        w.cross_kv = take(w.cross_kv_bytes);
         w.mel_before = take((size_t)B * T * 80 * 4);
         w.stop_logits = take((size_t)B * T * 4);
         w.lens = take(B * 4); w.finished = take(B * 4); w.scalars = take(64);
@@ -151,6 +157,7 @@ extern "C" int tts_destroy(TtsHandle* h) {
 extern "C" int tts_set_option(TtsHandle* h, const char* key, int64_t value) {
     if (!h || !key) return TTS_E_ARG;
     if (!strcmp(key, "decode_timestamps")) { h->decode_timestamps = value ? 1 : 0; return 0; }
+    if (!strcmp(key, "decode_debug")) { if (value < 0 || value > 8) FAIL(TTS_E_ARG, "decode_debug: 0 off, 1 + rank of the dumping CTA"); h->decode_debug = (int)value; return 0; }
     if (!strcmp(key, "cluster_group")) { if (value < 0 || value > CL_G) FAIL(TTS_E_ARG, "cluster_group must be 0 (auto) or 1..5"); h->cluster_group = (int)value; return 0; }
     if (!strcmp(key, "train_graph")) { h->train_graph = value ? 1 : 0; return 0; }
     if (!strcmp(key, "print_info")) { fprintf(stderr, "[tts_b200] sms=%d cluster_ok=%d max_clusters=%d group=%d ngroups=%d\n", h->num_sms, h->cluster_ok, h->max_clusters, h->cparams.G, h->cparams.ngroups); return 0; }
@@ -191,23 +198,18 @@ size_t pack_f32(Arena& ar, const float* v, size_t n, size_t npad = 0) {
 }
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// One segment of a cluster rank's weight stream (decode_cluster.cuh: cl_gemm).  rows[] lists the global output
-// row of every local column (NT tiles x 16; -1 = zero row).  Blocks are 16(n) x 32(k) in mma.sync m16n8k16
-// A-fragment order (2 x 32 lanes x uint4), ordered [chunk][warp][2] exactly as the consumer warps read them:
-//   typeB == false: warp w owns tile w % NT and K-slice kq = w / NT; chunk c holds its k-pairs kq*2*nchunks + 2c + {0,1}
-//   typeB == true : warp w owns tiles 2w, 2w+1; chunk c holds k-pair c of both (NT == 32)
-// kp_base offsets the k-pairs into W's K dimension (FFN2 K-slices).
+// One segment of a cluster rank's weight stream (decode_cluster.cuh: cl_gemm).  rows[] lists the global output row of every
+// local column (NT tiles x 16; -1 = zero row).  Warp w owns tiles w*TW .. w*TW + TW-1 over the k-pairs (32 columns each)
+// [kp_base, kp_base + KP); its run is [kp][j] blocks of 16(n) x 32(k) in mma.sync m16n8k16 A-fragment order (2 x 32 lanes x
+// uint4 = 1 KB), the warps' runs follow each other -- exactly the order the consumer warps read them.
 void pack_cluster_segment(std::vector<unsigned char>& out, const float* w, int N, int K, const std::vector<int>& rows,
-                          int kp_base, int KPT, int KSPLIT, bool typeB) {
+                          int kp_base, int KP, int TW) {
     const int NT = (int)rows.size() / 16;
-    const int nwarps = typeB ? 16 : NT * KSPLIT;
-    const int nchunks = typeB ? KPT : KPT / KSPLIT / 2;
     auto at = [&](int row, int k) -> uint32_t { return (row >= 0 && row < N && k < K) ? f2bf(w[(size_t)row * K + k]) : 0; };
-    for (int c = 0; c < nchunks; ++c)
-        for (int wi = 0; wi < nwarps; ++wi)
-            for (int j = 0; j < 2; ++j) {
-                const int tile = typeB ? 2 * wi + j : wi % NT;
-                const int kp = kp_base + (typeB ? c : (wi / NT) * 2 * nchunks + 2 * c + j);
+    for (int wi = 0; wi < NT / TW; ++wi)
+        for (int kpl = 0; kpl < KP; ++kpl)
+            for (int j = 0; j < TW; ++j) {
+                const int tile = wi * TW + j, kp = kp_base + kpl;
                 const size_t base = out.size();
                 out.resize(base + 1024, 0);
                 uint32_t* blk = reinterpret_cast<uint32_t*>(out.data() + base);
@@ -359,9 +361,9 @@ extern "C" int tts_finalize_weights(TtsHandle* h) {
         for (int rk = 0; rk < CL_SIZE; ++rk) {
             std::vector<unsigned char> seg;
             seg.reserve(CLW_RANK_BYTES);
-            pack_cluster_segment(seg, wf1, 256, 80, iota_rows(32 * rk, 32), 0, 4, 2, false);      // K 80 -> 128 (zeros)
-            pack_cluster_segment(seg, wf2, 256, 256, iota_rows(32 * rk, 32), 0, 8, 4, false);
-            pack_cluster_segment(seg, wpj, 512, 256, iota_rows(64 * rk, 64), 0, 8, 4, false);
+            pack_cluster_segment(seg, wf1, 256, 80, iota_rows(32 * rk, 32), 0, 4, 1);      // K 80 -> 128 (zeros)
+            pack_cluster_segment(seg, wf2, 256, 256, iota_rows(32 * rk, 32), 0, 8, 1);
+            pack_cluster_segment(seg, wpj, 512, 256, iota_rows(64 * rk, 64), 0, 8, 1);
             for (int l = 0; l < 6; ++l) {
                 const std::string p = "decoder.layers." + std::to_string(l);
                 if ((r = cat3(p + ".self_attn", w3, b3))) return r;
@@ -370,16 +372,16 @@ extern "C" int tts_finalize_weights(TtsHandle* h) {
                 GET(w1, p + ".ffn.w1.weight", (size_t)F * D); GET(w2, p + ".ffn.w2.weight", (size_t)D * F);
                 std::vector<int> qrows(192);                      // q, k, v (64 dims each) of head rk
                 for (int cc = 0; cc < 192; ++cc) qrows[cc] = (cc >> 6) * 512 + rk * 64 + (cc & 63);
-                pack_cluster_segment(seg, w3.data(), 3 * D, D, qrows, 0, 16, 1, false);
-                pack_cluster_segment(seg, wo, D, D, iota_rows(64 * rk, 64), 0, 16, 4, false);
-                pack_cluster_segment(seg, wq2, D, D, iota_rows(64 * rk, 64), 0, 16, 4, false);
-                pack_cluster_segment(seg, wo2, D, D, iota_rows(64 * rk, 64), 0, 16, 4, false);
-                pack_cluster_segment(seg, w1, F, D, iota_rows(256 * rk, 256), 0, 16, 1, false);
-                pack_cluster_segment(seg, w2, D, F, iota_rows(0, 512), 8 * rk, 8, 1, true);        // K-slice [256 rk, 256 rk + 256)
+                pack_cluster_segment(seg, w3.data(), 3 * D, D, qrows, 0, 16, 1);
+                pack_cluster_segment(seg, wo, D, D, iota_rows(64 * rk, 64), 0, 16, 1);
+                pack_cluster_segment(seg, wq2, D, D, iota_rows(64 * rk, 64), 0, 16, 1);
+                pack_cluster_segment(seg, wo2, D, D, iota_rows(64 * rk, 64), 0, 16, 1);
+                pack_cluster_segment(seg, w1, F, D, iota_rows(256 * rk, 256), 0, 16, 1);
+                pack_cluster_segment(seg, w2, D, F, iota_rows(0, 512), 8 * rk, 8, 2);          // K-slice [256 rk, 256 rk + 256), two tiles per warp
             }
             std::vector<int> hrows(16);
             for (int i = 0; i < 16; ++i) hrows[i] = (rk < 6 && 16 * rk + i < 81) ? 16 * rk + i : -1;
-            pack_cluster_segment(seg, whead.data(), 81, D, hrows, 0, 16, 8, false);
+            pack_cluster_segment(seg, whead.data(), 81, D, hrows, 0, 16, 1);
             if (seg.size() != CLW_RANK_BYTES) FAIL(TTS_E_STATE, "cluster weight stream size mismatch");
             memcpy(clw.data() + (size_t)rk * CLW_RANK_BYTES, seg.data(), CLW_RANK_BYTES);
         }
@@ -474,9 +476,9 @@ static int run_encoder(TtsHandle* h, void* ws, const Ws& L, const int64_t* ph, c
     }
     {   // cross K/V of all decoder layers -> cache [6][2][B][H][S][64]
         GemmParams p = gp(wsp<bf16>(ws, L.x), 512, h->ckv_w, 512, M, 6 * 1024, 512);
-        // rows S..Spad of every (layer, b, h) stay zero: the decode kernel copies whole 16-row V blocks
-        CKL(cudaMemsetAsync(wsp<bf16>(ws, L.cross_kv), 0, (size_t)6 * 2 * B * kHeads * L.Spad * kDHead * 2, st));
-        p.T = S; p.B = B; p.Lpad = L.Spad; p.bias = h->ckv_b; p.scatter = v_blocked ? SC_CROSS_KV_VT : SC_CROSS_KV; p.out_bf16 = wsp<bf16>(ws, L.cross_kv);
+        // rows past S of every (layer, b, h) stay zero: the decode kernel copies the cache at 16-row granularity
+        CKL(cudaMemsetAsync(wsp<bf16>(ws, L.cross_kv), 0, L.cross_kv_bytes, st));
+        p.T = S; p.B = B; p.Lpad = v_blocked ? L.nblk_cross * KV_BLOCK_ROWS : L.Spad; p.bias = h->ckv_b; p.scatter = v_blocked ? SC_CROSS_KV_VT : SC_CROSS_KV; p.out_bf16 = wsp<bf16>(ws, L.cross_kv);
         CKL(launch_gemm_tc(p, st));
     }
     return 0;
@@ -533,8 +535,8 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
                                                                           wsp<int>(ws, L.scalars), B, max_len);
     ++launch_counter();
     CK(cudaGetLastError());
-    // V blocks are copied whole (16 rows): rows not yet written must be finite, so the self cache starts zeroed
-    CK(cudaMemsetAsync(wsp<bf16>(ws, L.self_kv), 0, (size_t)6 * 2 * B * kHeads * L.Tpad * kDHead * 2, st));
+    // cache rows are copied at 16-row granularity: rows not yet written must be finite, so the self cache starts zeroed
+    CK(cudaMemsetAsync(wsp<bf16>(ws, L.self_kv), 0, L.self_kv_bytes, st));
 
     if (h->cluster_ok < 0) {                                            // how many 8-CTA clusters of this kernel can be co-resident?
         h->cluster_ok = 0;
@@ -552,33 +554,11 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
     if (h->cluster_ok != 1) FAIL(TTS_E_DEVICE, "device cannot co-schedule an 8-CTA cluster of the decode kernel");
 
     ClusterParams& cp = h->cparams; memset(&cp, 0, sizeof(cp));
-    cp.B = B; cp.Tmax = max_len; cp.S = S; cp.Tpad = L.Tpad; cp.Spad = L.Spad;
+    cp.B = B; cp.Tmax = max_len; cp.S = S; cp.nblk_self = L.nblk_self; cp.nblk_cross = L.nblk_cross;
     // utterances per cluster: as few as the co-resident cluster count allows (more SMs stream K/V), at most 8
     cp.G = h->cluster_group > 0 ? std::min(CL_G, h->cluster_group)
                                 : std::min(CL_G, std::max(1, (B + h->max_clusters - 1) / h->max_clusters));
     cp.ngroups = (B + cp.G - 1) / cp.G;
-    {   // TMA descriptors: cache as a 4-D bf16 tensor {64, Lpad, 8 heads, 12*B}, box {64, 16, 1, G}, no swizzle
-        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeFn encode = nullptr;
-        if (!encode) {
-            void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
-            CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-            if (!fn || qres != cudaDriverEntryPointSuccess) FAIL(TTS_E_DEVICE, "cuTensorMapEncodeTiled is not available");
-            encode = reinterpret_cast<EncodeFn>(fn);
-        }
-        auto make = [&](CUtensorMap* tm, void* base, int Lp) -> CUresult {
-            const cuuint64_t dims[4] = {64, (cuuint64_t)Lp, 8, (cuuint64_t)12 * B};
-            const cuuint64_t strides[3] = {128, (cuuint64_t)Lp * 128, (cuuint64_t)8 * Lp * 128};
-            const cuuint32_t box[4] = {64, CL_KV_ROWS, 1, (cuuint32_t)cp.G};
-            const cuuint32_t estr[4] = {1, 1, 1, 1};
-            return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        };
-        if (make(&cp.tm_self, wsp<bf16>(ws, L.self_kv), L.Tpad) != CUDA_SUCCESS || make(&cp.tm_cross, wsp<bf16>(ws, L.cross_kv), L.Spad) != CUDA_SUCCESS)
-            FAIL(TTS_E_ARG, "cuTensorMapEncodeTiled failed for the K/V caches");
-    }
     cp.seed = seed; cp.utt_offset = utt_offset; cp.dec_alpha = h->dec_alpha; cp.ln_eps = h->cfg.ln_eps; cp.pe = h->pe;
     cp.wpack = h->cl_wpack; cp.b_fc1 = h->pre_b1; cp.b_fc2 = h->pre_b2; cp.b_proj = h->pre_bp; cp.b_head = h->head_b;
     for (int l = 0; l < 6; ++l) {
@@ -605,6 +585,9 @@ extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* strea
     at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     h->cparams.ts = h->decode_timestamps ? wsp<unsigned long long>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).ts) : nullptr;
+    // (the debug dump lands in the `wide` activation buffer, idle during the decode loop: >= B * 2048 * 2 bytes per row of S/T)
+    h->cparams.dbg_rank = h->decode_debug - 1;
+    h->cparams.dbg = h->decode_debug ? wsp<float>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).wide) : nullptr;
     CK(cudaLaunchKernelEx(&cfg, decode_cluster_kernel, h->cparams, h->dec_t, n_steps));
     ++launch_counter();
     h->dec_t += n_steps;                                                // upper bound; tts_decode_status refines it
@@ -773,6 +756,17 @@ extern "C" int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long 
     CK(cudaMemcpyAsync(out, wsp<unsigned long long>(ws, L.ts), (size_t)(n_steps + 1) * 64 * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return 52;
+}
+
+extern "C" int tts_debug_read_dump(TtsHandle* h, void* ws, int64_t offset, int64_t n, float* out_host, void* stream) {
+    if (!h || !ws || !out_host || offset < 0 || n <= 0) return TTS_E_ARG;
+    if (!h->dec_active) FAIL(TTS_E_STATE, "no decode session");
+    const Ws L = Ws::make(h->dec_B, h->dec_S, h->dec_T);
+    const size_t cap = (size_t)h->dec_B * (size_t)std::max(h->dec_S, h->dec_T) * 2048 * 2 / 4;
+    if ((size_t)(offset + n) > cap) FAIL(TTS_E_ARG, "dump range exceeds the debug buffer");
+    CK(cudaMemcpyAsync(out_host, wsp<float>(ws, L.wide) + offset, (size_t)n * 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
 }
 
 // per-kernel test entry points

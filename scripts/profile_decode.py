@@ -41,10 +41,16 @@ for lo, hi in ((1, 50), (T // 2 - 25, T // 2 + 25), (T - 50, T)):
         print(f"   {k:11s} {row[k]:7.2f} us/phase x{len(groups[k]):2d} = {tot[k]:7.1f} us/step")
 a = m.all_stamps.double()
 if (a[:, 52] > 0).any():
-    w = a[T // 2 - 100: T // 2 + 100]
-    print("O-proj L0 breakdown (us): gemm->52 %.2f | push %.2f | cl_sync %.2f | LN %.2f" % (
-        float((w[:, 52] - w[:, 4]).mean() / 1e3), float((w[:, 53] - w[:, 52]).mean() / 1e3),
-        float((w[:, 54] - w[:, 53]).mean() / 1e3), float((w[:, 5] - w[:, 54]).mean() / 1e3)))
+    for name, w in (("t~400", a[T // 2 - 100: T // 2 + 100]), ("t~750", a[T - 100: T - 5])):
+        d = lambda i, j: float((w[:, i] - w[:, j]).mean() / 1e3)
+        print(f"[{name}] layer 0, us:")
+        print("  self-attn: loop %.2f | partial bar %.2f | merge+push %.2f | gather %.2f" % (d(61, 3), d(62, 61), d(63, 62), d(4, 63)))
+        print("  O-proj   : gemm+epi %.2f | push %.2f | gather %.2f | LN %.2f" % (d(52, 4), d(53, 52), d(54, 53), d(5, 54)))
+        print("  cross    : q2 gemm+bar %.2f | loop %.2f | partial bar %.2f | merge+push %.2f | gather %.2f" % (d(6, 5), d(64, 6), d(65, 64), d(66, 65), d(7, 66)))
+        print("  rs push detail: bar->index math %.2f | ybuf LDS %.2f | 1st st.async %.2f | rest %.2f" % (d(72, 56), d(70, 72), d(71, 70), d(57, 71)))
+        print("  warp-0 GEMM (wait for stage | MMA loop): O-proj %.2f | %.2f   FFN1 %.2f | %.2f   FFN2 %.2f | %.2f" % (d(74, 73), d(75, 74), d(77, 76), d(78, 77), d(80, 79), d(81, 80)))
+        print("  FFN      : ffn1 %.2f | ffn2 gemm %.2f | bar %.2f | rs push %.2f | rs gather %.2f | reduce+y3 push %.2f | y3 gather %.2f | LN %.2f" % (
+            d(9, 8), d(55, 9), d(56, 55), d(57, 56), d(58, 57), d(59, 58), d(60, 59), d(10, 60)))
 print("mean us/step", out["us_per_step_mean"], " roofline us/step", decode_bytes(B, T, S) / T / 6468.6e3)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/phase_times.json", "w"), indent=1)

@@ -45,6 +45,7 @@ constexpr int CL_STAGES = 5, CL_STAGE_BYTES = 32768;
 // the test can only be fooled by a warp >= 10 stages ahead of the landed data, and the block-wide barriers after every
 // segment (and the in-order waits inside an attention segment: G + 5 <= 10) keep every reader closer than that.
 constexpr int CL_FULL_BARS = 2 * CL_STAGES;
+constexpr int CL_TS_COLS = 128;                      // %globaltimer stamps per decoder step (profiling aid): 0..51 phases, 52.. fine-grained
 constexpr int CL_NS = 512 / CL_SIZE;                 // 64: columns of a 512-wide output owned by one rank
 constexpr int KV_BLOCK_ROWS = 64, KV_BLOCK_ELEMS = 8192;     // one cache block: 64 rows of K + 64 rows of V = 16 KB
 constexpr int KV_STAGE_ROWS = 128;                   // rows of one pair per ring stage (two blocks)
@@ -91,7 +92,7 @@ struct ClusterParams {
     const bf16* cross_kv;                        // [6][B][8][nblk_cross][KV_BLOCK_ELEMS]
     const int* plens;
     float* mel_before; float* stop_logits; int* lens; int* finished; int* n_finished;
-    unsigned long long* ts;                      // optional [Tmax][64] %globaltimer stamps (cluster 0, rank 0)
+    unsigned long long* ts;                      // optional [Tmax][CL_TS_COLS] %globaltimer stamps (cluster 0, rank 0)
     int dbg_rank;
     float* dbg;                                  // optional debug dump (cluster 0, rank dbg_rank, first step of the launch): slots of 2560 floats
 };
@@ -135,6 +136,14 @@ TTS_D void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar
 TTS_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+// %globaltimer read placed behind a shared-memory load (see the stamp lambda of the kernel)
+TTS_D unsigned long long timer_after_lds(const void* smem_word) {
+    unsigned long long now; uint32_t dummy;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dummy) : "r"(smem_u32(smem_word)) : "memory");
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "r"(dummy) : "memory");                // input operand: issues after the load returned
+    return now;
 }
 
 // ---------------------------------------------------------------- per-CTA context (consumer side)
@@ -261,7 +270,7 @@ TTS_D void cl_release(const ClCtx& c, uint32_t idx) {
 // registers (NCH independent MMA chains per tile).  epi(tile, n, m, value) receives complete sums (+ bias).  No block-level
 // barrier inside: callers synchronise where the results are consumed.
 template <int KP, int TW, class BiasFn, class Epi>
-TTS_D void cl_gemm(ClCtx& c, int na, const bf16* X, int ldx, BiasFn biasf, Epi epi) {
+TTS_D void cl_gemm(ClCtx& c, int na, const bf16* X, int ldx, BiasFn biasf, Epi epi, unsigned long long* tstamp = nullptr) {
     constexpr int BW = TW * KP * 1024, WPS = CL_STAGE_BYTES / BW;
     constexpr int NCH = (TW == 1 && KP >= 16) ? 4 : 2;
     const int nst = (na + WPS - 1) / WPS;
@@ -276,7 +285,9 @@ TTS_D void cl_gemm(ClCtx& c, int na, const bf16* X, int ldx, BiasFn biasf, Epi e
 #pragma unroll
             for (int q = 0; q < NCH; ++q) { acc[j][q][0] = acc[j][q][1] = acc[j][q][2] = acc[j][q][3] = 0.f; }
         const uint32_t idx = c.consumed + (uint32_t)(c.warp / WPS);
+        if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory"); tstamp[0] = now; }
         const uint4* wp = reinterpret_cast<const uint4*>(cl_acquire(c, idx) + (c.warp % WPS) * BW);
+        if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "l"(wp) : "memory"); tstamp[1] = now; }
         const bf16* xrow = X + (c.lane & 7) * ldx + (c.lane >> 3) * 8;
 #pragma unroll
         for (int kp = 0; kp < KP; ++kp) {
@@ -291,6 +302,7 @@ TTS_D void cl_gemm(ClCtx& c, int na, const bf16* X, int ldx, BiasFn biasf, Epi e
                 mma_bf16_16816(acc[j][kp % NCH], a1, bfrag[2], bfrag[3]);
             }
         }
+        if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(acc[0][0][0]), "f"(acc[TW - 1][NCH - 1][3]) : "memory"); tstamp[2] = now; }
         cl_release(c, idx);
         const int m0 = t4 * 2;
 #pragma unroll
@@ -419,7 +431,7 @@ TTS_D void cl_layernorm(ClCtx& c, float ln_eps) {
 // with an online softmax per warp.  self: cache rows 0..t-1 plus the newest row (k_t, v_t) from qkvbuf; cross: rows 0..len-1.
 // The pair's first warp merges the three partials (+ the newest row) in fixed order and pushes the pair's 64 outputs as bf16
 // into abuf[gi][rank*64 ..] of every CTA.
-TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, const volatile int* glens) {
+TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, const volatile int* glens, unsigned long long* stamp_row) {
     const float* qkv = reinterpret_cast<const float*>(c.smem + SM_QKV);
     float* part = reinterpret_cast<float*>(c.smem + SM_AMERGE) + c.warp * 68;
     const int g = c.lane >> 2, t4 = c.lane & 3;
@@ -515,7 +527,9 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, cons
         if (c.lane == 0) { part[64] = m; part[65] = ls; }
     }
     c.consumed += (uint32_t)(nj * c.G);
+    if (stamp_row) stamp_row[self ? 61 : 64] = timer_after_lds(c.smem + SM_MISC + 192);
     consumer_bar();
+    if (stamp_row) stamp_row[self ? 62 : 65] = timer_after_lds(c.smem + SM_MISC + 192);
     if (active && wv == 0) {                             // merge the pair's three partials (+ the newest row) in fixed order
         const float* pa = part;
         float mm = fmaxf(fmaxf(pa[64], pa[68 + 64]), pa[136 + 64]);
@@ -557,6 +571,7 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, cons
                         pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w), map_to_rank(bar, (uint32_t)peer));
         }
     }
+    if (stamp_row) stamp_row[self ? 63 : 66] = timer_after_lds(c.smem + SM_MISC + 192);
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -591,9 +606,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
     const bool stamper = p.ts != nullptr && cid == 0 && c.rank == 0 && c.tid == 0;
     auto stamp = [&](int t, int idx) {
         if (stamper) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            p.ts[(size_t)t * 64 + idx] = now;
+            // BAR.SYNC does not block at issue (the warp stalls at the next instruction that touches barrier-protected state): a
+            // shared-memory load in front of the timer read makes the stamp the barrier's RELEASE time, not its issue time
+            unsigned long long now; uint32_t dummy;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(dummy) : "r"(smem_u32(cl_smem + SM_MISC + 192)) : "memory");
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "r"(dummy) : "memory");      // input operand: issues after the load returned
+            p.ts[(size_t)t * CL_TS_COLS + idx] = now;
         }
     };
 
@@ -697,7 +715,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     consumer_bar();
                     stamp(t, 3 + 8 * l);
                     if (l == 0) dbg_dump(t, 1, qkvb, 192, 192, false);
-                    cl_attention(p, c, true, t, glens);
+                    cl_attention(p, c, true, t, glens, (stamper && l == 0) ? p.ts + (size_t)t * CL_TS_COLS : nullptr);
                     gather_sync(c);
                     stamp(t, 4 + 8 * l);
                     if (l == 0) dbg_dump(t, 2, abuf, LDX512, 512, true);
@@ -705,10 +723,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     ln_prefetch(c, W.ln1g, W.ln1b);
                     cl_gemm<16, 1>(c, 4, abuf, LDX512,
                             [&](int ti, int n) { return __ldg(W.bo + c.rank * CL_NS + ti * 16 + n); },
-                            [&](int ti, int n, int m, float v) { wst[m * 16 + n] = v + xres[m * 512 + c.rank * CL_NS + ti * 16 + n]; });
+                            [&](int ti, int n, int m, float v) { wst[m * 16 + n] = v + xres[m * 512 + c.rank * CL_NS + ti * 16 + n]; },
+                            (stamper && l == 0) ? p.ts + (size_t)t * CL_TS_COLS + 73 : nullptr);
+                    if (l == 0) stamp(t, 52);
                     if (c.warp < 4) { __syncwarp(); push_tile_f32(c, wst, ybuf + c.rank * CL_NS + c.warp * 16, 512); }
+                    if (l == 0) stamp(t, 53);
                     cp_async_wait<0>();
                     gather_sync(c);
+                    if (l == 0) stamp(t, 54);
                     cl_layernorm(c, p.ln_eps);
                     stamp(t, 5 + 8 * l);
                     if (l == 0) dbg_dump(t, 3, xa, LDX512, 512, true);
@@ -718,7 +740,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                             [&](int ti, int n, int m, float v) { qkvb[m * 192 + ti * 16 + n] = v; });
                     consumer_bar();
                     stamp(t, 6 + 8 * l);
-                    cl_attention(p, c, false, t, glens);
+                    cl_attention(p, c, false, t, glens, (stamper && l == 0) ? p.ts + (size_t)t * CL_TS_COLS : nullptr);
                     gather_sync(c);
                     stamp(t, 7 + 8 * l);
                     if (l == 0) dbg_dump(t, 4, abuf, LDX512, 512, true);
@@ -735,27 +757,36 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     // ---- FFN: hidden slice [256 rank, +256) stays local (bf16); FFN2 is split along K
                     cl_gemm<16, 1>(c, 16, xa, LDX512,
                             [&](int ti, int n) { return __ldg(W.b1 + c.rank * 256 + ti * 16 + n); },
-                            [&](int ti, int n, int m, float v) { hbuf[m * LDX256 + ti * 16 + n] = __float2bfloat16(fmaxf(v, 0.f)); });
+                            [&](int ti, int n, int m, float v) { hbuf[m * LDX256 + ti * 16 + n] = __float2bfloat16(fmaxf(v, 0.f)); },
+                            (stamper && l == 0) ? p.ts + (size_t)t * CL_TS_COLS + 76 : nullptr);
                     consumer_bar();
                     stamp(t, 9 + 8 * l);
                     if (l == 0) dbg_dump(t, 6, hbuf, LDX256, 256, true);
                     // partial sums over this rank's 256 hidden units, staged in ybuf (free between LN2 and the y3 gather)
                     ln_prefetch(c, W.ln3g, W.ln3b);
                     cl_gemm<8, 2>(c, 16, hbuf, LDX256, [&](int, int) { return 0.f; },
-                            [&](int ti, int n, int m, float v) { ybuf[m * 512 + ti * 16 + n] = v; });
+                            [&](int ti, int n, int m, float v) { ybuf[m * 512 + ti * 16 + n] = v; },
+                            (stamper && l == 0) ? p.ts + (size_t)t * CL_TS_COLS + 79 : nullptr);
+                    if (l == 0) stamp(t, 55);
                     consumer_bar();
+                    if (l == 0) stamp(t, 56);
                     if (l == 0) dbg_dump(t, 8, ybuf, 512, 512, false);
                     {
                         const uint32_t bar = gather_bar(c);
                         for (int i = c.tid; i < CL_SIZE * c.G * 16; i += CL_CONSUMERS) {   // reduce-scatter: 64 columns to each peer
                             const int peer = i / (c.G * 16), j = i % (c.G * 16), m = j >> 4, pc = j & 15;
+                            if (l == 0 && i == 0 && stamper) p.ts[(size_t)t * CL_TS_COLS + 72] = timer_after_lds(cl_smem + SM_MISC + 192) + (unsigned long long)(peer + m + pc) * 0ull;
                             const float4 v = *reinterpret_cast<const float4*>(ybuf + m * 512 + peer * CL_NS + pc * 4);
+                            if (l == 0 && i == 0 && stamper) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(v.x) : "memory"); p.ts[(size_t)t * CL_TS_COLS + 70] = now; }
                             st_async_v4(map_to_rank(smem_u32(recv + (c.rank * CL_G + m) * CL_NS + pc * 4), (uint32_t)peer),
                                         __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w),
                                         map_to_rank(bar, (uint32_t)peer));
+                            if (l == 0 && i == 0) stamp(t, 71);
                         }
                     }
+                    if (l == 0) stamp(t, 57);
                     gather_sync(c);
+                    if (l == 0) stamp(t, 58);
                     if (l == 0) dbg_dump(t, 10, recv, 2560, 2560, false);
                     if (c.tid < c.G * 16) {              // my 64 columns: 8 partials (fixed order) + bias + residual -> every peer's ybuf
                         const int m = c.tid >> 4, pc = c.tid & 15, col = c.rank * CL_NS + pc * 4;
@@ -773,8 +804,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                             st_async_v4(map_to_rank(smem_u32(ybuf + m * 512 + col), (uint32_t)peer), __float_as_uint(v.x), __float_as_uint(v.y),
                                         __float_as_uint(v.z), __float_as_uint(v.w), map_to_rank(bar, (uint32_t)peer));
                     }
+                    if (l == 0) stamp(t, 59);
                     cp_async_wait<0>();
                     gather_sync(c);
+                    if (l == 0) stamp(t, 60);
                     if (l == 0) dbg_dump(t, 9, ybuf, 512, 512, false);
                     cl_layernorm(c, p.ln_eps);
                     stamp(t, 10 + 8 * l);

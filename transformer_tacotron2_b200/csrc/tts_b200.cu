@@ -104,7 +104,7 @@ struct Ws {
         w.mel_before = take((size_t)B * T * 80 * 4);
         w.stop_logits = take((size_t)B * T * 4);
         w.lens = take(B * 4); w.finished = take(B * 4); w.scalars = take(64);
-        w.ts = take((size_t)(T + 1) * 64 * 8);
+        w.ts = take((size_t)(T + 1) * CL_TS_COLS * 8);
         w.x = take(M * 512 * 2); w.x2 = take(M * 512 * 2); w.wide = take(M * 2048 * 2); w.a = take(M * 512 * 2);
         w.y = take(M * 512 * 4); w.mel16 = take(M * 96 * 2); w.mel32 = take(M * 80 * 4);
         w.ph = take((size_t)B * S * 8); w.plens = take(B * 4); w.mlens = take(B * 4);
@@ -753,7 +753,7 @@ extern "C" int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long 
     if (!h || !ws || !out || n_steps <= 0) return TTS_E_ARG;
     if (!h->dec_active || n_steps != h->dec_T) FAIL(TTS_E_STATE, "no decode session / n_steps must equal max_len");
     const Ws L = Ws::make(h->dec_B, h->dec_S, h->dec_T);
-    CK(cudaMemcpyAsync(out, wsp<unsigned long long>(ws, L.ts), (size_t)(n_steps + 1) * 64 * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaMemcpyAsync(out, wsp<unsigned long long>(ws, L.ts), (size_t)(n_steps + 1) * CL_TS_COLS * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return 52;
 }

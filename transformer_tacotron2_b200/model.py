@@ -330,7 +330,7 @@ class TransformerTTS(nn.Module):
 
     def phase_timestamps(self, n_steps: int) -> torch.Tensor:
         """[n_steps, n_phases] int64 ns stamps of the last persistent decode (option decode_timestamps = 1)."""
-        out = torch.zeros(n_steps + 1, 64, dtype=torch.int64)     # last row: fine-grained debug stamps
+        out = torch.zeros(n_steps + 1, 128, dtype=torch.int64)     # last row: fine-grained debug stamps
         n = self._lib.tts_debug_phase_timestamps(self._handle, self._ws.data_ptr(), out.data_ptr(), n_steps, self._stream())
         if n <= 0:
             raise _lib.TtsError(f"tts_debug_phase_timestamps failed ({n})")

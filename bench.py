@@ -191,10 +191,17 @@ def run_reference(args, rank):
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from transformer_tacotron2_b200 import _lib
+    import datetime
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # short collective timeout: a rank that dies must not park its peers in a barrier for the default 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=args.nccl_timeout))
+    from transformer_tacotron2_b200 import _lib as _libmod
+    if world > 1:                                                   # one builder per node, then everybody loads the finished library
+        if local_rank == 0:
+            _libmod.load()
+        dist.barrier()
     T, S = args.frames, args.phonemes
     B = args.batch if args.scaling == "weak" else max(1, args.batch // world)
     utt0 = rank * B
@@ -204,6 +211,7 @@ def run_b200(args, rank, world, local_rank):
     model.load_state_dict(src.state_dict())
     model.sync_weights()
     lib = _lib.load()
+    extra = {}
     ph_all, pl_all = synthetic_inputs(B * world, S, DATA_SEED)
     ph, pl = ph_all[utt0:utt0 + B].contiguous(), pl_all[utt0:utt0 + B].contiguous()
     ph_d, pl_d = ph.to(dev), pl.to(dev)
@@ -258,6 +266,51 @@ def run_b200(args, rank, world, local_rank):
     e2e = frames_total / e2e_s
     h2d = B * S * 8 + B * 4
     d2h = B * T * 80 * 4 + B * T * 4 + B * 4
+
+    # ---- the other configurations of BASELINE.json, same timing rules, each with its own decode-kernel roofline ---------------
+    def measure_case(name, Bc, Sc, Tc, utt_off, steps, desc):
+        """device-resident inference of Bc utterances on THIS rank -> (ms per inference, decode-kernel ms)"""
+        phc, plc = synthetic_inputs(Bc, Sc, DATA_SEED + 17)
+        phc, plc = phc.to(dev), plc.to(dev)
+        model.profile_events = True
+        for _ in range(3):
+            o = model.inference(phc, plc, max_len=Tc, seed=DROPOUT_SEED, utt_offset=utt_off)
+        assert int(o[1].min()) == Tc
+        model.decode_ms.clear()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            model.inference(phc, plc, max_len=Tc, seed=DROPOUT_SEED, utt_offset=utt_off)
+        b.record()
+        barrier()
+        ms = max_over_ranks(a.elapsed_time(b)) / steps
+        dms = max_over_ranks(statistics.mean(model.decode_ms))
+        model.profile_events = False
+        return ms, dms
+
+    def case_line(desc, Bc, Sc, Tc, nranks, ms, dms):
+        peak_, _k = measured_peaks()
+        algo_ = decode_bytes(Bc, Tc, Sc)
+        ach = algo_ / (dms * 1e-3) / 1e9
+        return {"value": nranks * Bc * Tc / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "config": {"workload": desc, "batch_per_gpu": Bc, "phonemes": Sc, "frames": Tc},
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_, "unit": "GB/s", "frac": ach / peak_, "algorithmic_bytes_per_launch": algo_,
+                             "kernel_ms_per_launch": dms, "us_per_decoder_step": 1e3 * dms / Tc}}
+
+    if not args.no_extra:
+        ksteps = max(2, args.steps // 4)
+        # configs[2] as BASELINE.json words it: a FIXED batch of 64 utterances sharded over the N GPUs (strong scaling)
+        Bs = max(1, args.batch // world)
+        ms, dms = measure_case("strong", Bs, S, T, rank * Bs, ksteps, "")
+        extra["strong"] = case_line(f"configs[2] strong scaling: 64 utterances sharded over {world} GPU(s), {Bs} per GPU, S={S}, {T} frames", Bs, S, T, world, ms, dms)
+        extra["strong"]["scaling"] = "strong"
+        # configs[1]: batch-1 latency path (every rank decodes one utterance; value = one GPU's frames/s, latency per frame beside it)
+        ms, dms = measure_case("latency_b1", 1, S, T, rank, ksteps, "")
+        extra["latency_b1"] = case_line(f"configs[1]: greedy AR, batch 1, S={S}, {T} frames, latency path (per GPU)", 1, S, T, 1, ms, dms)
+        extra["latency_b1"]["us_per_frame"] = 1e3 * ms / T
+        # configs[4]: long utterances, batch 16 per GPU, 300 phonemes -> 1600 frames
+        ms, dms = measure_case("long", 16, 300, 1600, rank * 16, 2, "")
+        extra["long"] = case_line("configs[4]: long-utterance inference, B=16/GPU, S=300, 1600 frames", 16, 300, 1600, world, ms, dms)
 
     # ---- second half of BASELINE.json's metric: teacher-forced train step (configs[3]: B = 32 per GPU, data parallel,
     #      one NCCL all-reduce over the flat gradient buffer per step), utterances / s over all ranks -------------------
@@ -335,13 +388,12 @@ def run_b200(args, rank, world, local_rank):
     }
     if train is not None:
         line["train"] = train
+    line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, desc = cpu_oracle_sample(B, S, T, window=args.cpu_window, threads=threads)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        pass
 
 
 def main():
@@ -359,6 +411,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step measurement (the `train` key)")
     ap.add_argument("--train-batch", type=int, default=32)
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling / batch-1 latency / long-utterance lines")
+    ap.add_argument("--nccl-timeout", type=int, default=180, help="seconds before a collective gives up (a dead rank must not stall the job)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -370,10 +424,14 @@ def main():
         return
     try:
         run_b200(args, rank, world, local_rank)
-    finally:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            dist.destroy_process_group()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush(); sys.stdout.flush()
+        os._exit(1)                                                 # fail fast: no barrier, no destroy_process_group on a broken context
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

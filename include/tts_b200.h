@@ -107,6 +107,13 @@ int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* 
                 const float* mels, const int32_t* mel_lens, int B, int S, int T, uint64_t seed, int utt_offset,
                 float* mel_before, float* mel_after, float* stop_logits, void* stream);
 
+/* Forced ("step-locked") decoding: overwrite frame t (< frames decoded so far) of the session's mel_before buffer with
+ * frames [B][80] fp32 (device memory).  The next tts_decode_steps() call resumes from frame t_done - 1, so writing frame
+ * t_done - 1 between single-step calls feeds the decoder somebody else's trajectory (the parity tests feed the oracle's). */
+int tts_decode_set_frame(TtsHandle* h, void* ws, int t, const float* frames, void* stream);
+/* Read frame t of the session back: frames [B][80] fp32 (mel_before) and, if not NULL, stop_logits [B] (device memory). */
+int tts_decode_get_frame(TtsHandle* h, void* ws, int t, float* frames, float* stop_logits, void* stream);
+
 /* Profiling aid: with option "decode_timestamps" = 1 the persistent decode kernel stamps %globaltimer
  * after every phase; this copies [n_steps][n_phases] stamps (ns) to the host and returns n_phases. [sync] */
 int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long long* out, int n_steps, void* stream);
@@ -151,6 +158,20 @@ int tts_train_num_tensors(TtsHandle* h);
 int tts_train_tensor_info(TtsHandle* h, int index, const char** name, int64_t* offset, int64_t* numel, int* is_buffer);
 /* Copy a range of the parameter (which = 0), gradient (1) or running-statistics (2) buffer to the host. [sync] */
 int tts_train_read(TtsHandle* h, int which, int64_t offset, int64_t numel, float* host_out);
+/* Overwrite a range of the parameter (which = 0) or running-statistics (2) buffer from the host; parameters take effect after
+ * tts_train_repack() (which refreshes the bf16 operand copies). [sync] */
+int tts_train_write(TtsHandle* h, int which, int64_t offset, int64_t numel, const float* host_in);
+
+/* ---- autograd bridge (the module's train-mode forward(): oracle `model.train(); out = model(...); loss.backward()`) ----------
+ * tts_train_forward: the train-mode forward of tts_train_step alone (batch-statistics BatchNorm, every dropout site on); the
+ *   activations stay in the workspace, the outputs are read with tts_train_outputs().
+ * tts_train_backward: back-propagates caller-supplied output gradients d_before [B][T][80], d_after [B][T][80], d_stop [B][T]
+ *   (fp32, device memory: dLoss/d(mel_before), dLoss/d(mel_after), dLoss/d(stop_logits) of ANY loss) through that forward into the
+ *   flat gradient buffer (tts_train_grads).  Same workspace, shape, seed, utt_offset and p_residual as the forward it follows. */
+int tts_train_forward(TtsHandle* h, void* workspace, const int64_t* phonemes, const int32_t* phoneme_lens, const float* mels,
+                      const int32_t* mel_lens, int B, int S, int T, uint64_t seed, int utt_offset, double p_residual, void* stream);
+int tts_train_backward(TtsHandle* h, void* workspace, int B, int S, int T, int utt_offset, double p_residual,
+                       const float* d_before, const float* d_after, const float* d_stop, void* stream);
 
 /* ---- per-kernel entry points (tests/test_gpu_kernels.py; not part of the drop-in surface) ---- */
 /* C[M][N] = act(A[M][K] . W[N][K]^T + bias) ; bf16 in, fp32 out; act 0 none / 1 relu / 2 tanh (tcgen05 kernel, gemm_tc.cuh). */

@@ -245,3 +245,50 @@ def test_train_step_vs_committed_golden(oracle_model):
             if float(want.norm()) > 1e-3 * total and want.numel() > 1:
                 assert rel_l2(grads[key[5:]], want) < TOL_GRAD, key
     assert torch.allclose(tr.buffers()["postnet.convs.0.bn.running_mean"], torch.from_numpy(g["bn0_running_mean"]), atol=2e-2, rtol=2e-2)
+
+
+def test_module_train_mode_forward_autograd(oracle_model):
+    """SURVEY.md 8(b): the boundary is the nn.Module -- `model.train(); out = model(...); loss_fn(*out).backward();
+    torch.optim.X(model.parameters()).step()` works on the B200 module as on the oracle (autograd bridge over
+    tts_train_forward / tts_train_backward), with ANY loss on the outputs."""
+    from oracle import synthetic
+    from oracle.transformer_tts import tts_loss
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    inputs = synthetic.make_inputs(3, 24, 60, 77, ragged=True)
+    ph, pl, mels, ml = inputs
+    om, oout, oloss, ograds = _oracle_step(oracle_model, inputs, seed=5)
+    g = make_b200_model(oracle_model).train()
+    out = g(ph, pl, mels, ml, seed=5)
+    assert all(t.requires_grad for t in out)
+    for a, b in zip(out, oout):
+        assert rel_l2(a, b) < TOL_OUT
+    loss = tts_loss(*[t.cpu() for t in out], mels, ml)
+    assert abs(float(loss) - float(oloss)) < TOL_LOSS * abs(float(oloss))
+    loss.backward()
+    num = sum(float((p.grad - ograds[k]).norm() ** 2) for k, p in g.named_parameters()) ** 0.5
+    den = sum(float(v.norm() ** 2) for v in ograds.values()) ** 0.5
+    print(f"autograd bridge: loss {float(loss):.4f} (oracle {float(oloss):.4f}), whole-gradient rel-L2 {num / den:.4f}")
+    assert num / den < TOL_GRAD_ALL
+    # BatchNorm running statistics moved exactly as the oracle's
+    assert rel_l2(g.postnet.convs[0].bn.running_mean, om.postnet.convs[0].bn.running_mean) < 2e-2
+    # a different loss (sum of the stop logits): gradient only behind the stop head path
+    g.zero_grad()
+    out = g(ph, pl, mels, ml, seed=5)
+    out[2].sum().backward()
+    assert float(g.stop_linear.weight.grad.norm()) > 0 and float(g.mel_linear.weight.grad.norm()) == 0.0
+    # an optimiser step on the module's parameters is picked up by the next forward, and by eval-mode inference
+    opt = torch.optim.SGD(g.parameters(), lr=1e-2)
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        out = g(ph, pl, mels, ml, seed=5)
+        loss = tts_loss(*[t.cpu() for t in out], mels, ml)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    print("autograd bridge losses:", [round(x, 4) for x in losses])
+    assert losses[-1] < losses[0]
+    g.eval()
+    a = g.inference(ph, pl, max_len=8, seed=1)
+    assert torch.isfinite(a[0]).all()

@@ -36,6 +36,8 @@ SIGNATURES = {
     "tts_decode_steps": (_I, [_P, _P, _I, _P]),
     "tts_decode_status": (_I, [_P, _P, C.POINTER(_I), C.POINTER(_I), _P]),
     "tts_decode_end": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
+    "tts_decode_set_frame": (_I, [_P, _P, _I, _P, _P]),
+    "tts_decode_get_frame": (_I, [_P, _P, _I, _P, _P, _P]),
     "tts_infer_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _U64, _I, _P, _P, _P, C.POINTER(_I), _P]),
     "tts_forward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _U64, _I, _P, _P, _P, _P]),
     "tts_debug_phase_timestamps": (_I, [_P, _P, _P, _I, _P]),
@@ -54,6 +56,9 @@ SIGNATURES = {
     "tts_train_num_tensors": (_I, [_P]),
     "tts_train_tensor_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I)]),
     "tts_train_read": (_I, [_P, _I, _I64, _I64, _P]),
+    "tts_train_write": (_I, [_P, _I, _I64, _I64, _P]),
+    "tts_train_forward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _U64, _I, C.c_double, _P]),
+    "tts_train_backward": (_I, [_P, _P, _I, _I, _I, _I, C.c_double, _P, _P, _P, _P]),
     "tts_k_gemm": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "tts_k_conv5": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "tts_k_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

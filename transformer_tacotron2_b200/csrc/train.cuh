@@ -366,14 +366,16 @@ int tr_conv_bwd(TrCtx& c, const TrConv& cv, const TD* dout, int ldd, const float
     return 0;
 }
 
-int train_forward_backward(TrCtx& c, float* loss_out, float pos_weight) {
+// The training step in three parts (tts_train_step runs all three; the module's autograd bridge -- tts_train_forward /
+// tts_train_backward -- runs the first and, with the caller's output gradients, the third).
+// ---- train-mode forward: every activation the backward pass needs stays in the workspace
+int train_forward(TrCtx& c) {
     TtsHandle* h = c.h; TtsTrain* t = c.t; TrWs& w = c.w; cudaStream_t st = c.st;
     const int B = c.B, S = c.S, T = c.T, Me = B * S, Md = B * T;
     const float eps = h->cfg.ln_eps;
     const int* plens = w.plens; const int* mlens = w.mlens;
     const int64_t* ph = w.ph_in; const float* mels = w.mels_in;
-    TRL(cudaMemsetAsync(c.G, 0, t->n * 4, st));
-
+    (void)eps; (void)mels;
     // ================================================================ forward (train mode)
     embed_kernel<<<(Me + 3) / 4, 256, 0, st>>>(ph, plens, t->mats[t->embed].fwd, w.e[0], B, S, h->cfg.n_vocab);
     ++launch_counter();
@@ -454,6 +456,17 @@ int train_forward_backward(TrCtx& c, float* loss_out, float pos_weight) {
     add_kernel<<<(unsigned)(((long)Md * 80 + 255) / 256), 256, 0, st>>>(w.mel_before, w.p5, w.mel_after, (long)Md * 80);
     ++launch_counter();
 
+    TRL(cudaGetLastError());
+    return 0;
+}
+// ---- loss P13 and its gradient with respect to (mel_before, mel_after, stop_logits) -> w.dbefore / w.dafter / w.dstop
+int train_loss(TrCtx& c, float* loss_out, float pos_weight) {
+    TtsHandle* h = c.h; TtsTrain* t = c.t; TrWs& w = c.w; cudaStream_t st = c.st;
+    const int B = c.B, S = c.S, T = c.T, Me = B * S, Md = B * T;
+    const float eps = h->cfg.ln_eps;
+    const int* plens = w.plens; const int* mlens = w.mlens;
+    const int64_t* ph = w.ph_in; const float* mels = w.mels_in;
+    (void)h; (void)t; (void)S; (void)Me; (void)eps; (void)plens; (void)ph;
     // ================================================================ loss (P13) and its gradient
     TRL(cudaMemsetAsync(w.acc, 0, 64, st));
     loss_kernel<<<std::min<long>(((long)Md * 81 + 255) / 256, 2368), 256, 0, st>>>(w.mel_before, w.mel_after, w.stop, mels, mlens, B, T, pos_weight, w.acc, w.dbefore,
@@ -462,6 +475,17 @@ int train_forward_backward(TrCtx& c, float* loss_out, float pos_weight) {
     launch_counter() += 2;
     TRL(cudaGetLastError());
 
+    return 0;
+}
+// ---- backward from the output gradients in w.dbefore [Md][80], w.dafter [Md][80], w.dstop [Md] (fp32) into the flat gradient buffer
+int train_backward(TrCtx& c) {
+    TtsHandle* h = c.h; TtsTrain* t = c.t; TrWs& w = c.w; cudaStream_t st = c.st;
+    const int B = c.B, S = c.S, T = c.T, Me = B * S, Md = B * T;
+    const float eps = h->cfg.ln_eps;
+    const int* plens = w.plens; const int* mlens = w.mlens;
+    const int64_t* ph = w.ph_in; const float* mels = w.mels_in;
+    (void)mels;
+    TRL(cudaMemsetAsync(c.G, 0, t->n * 4, st));
     // ================================================================ backward
     // postnet: d mel_after flows into conv 4 .. 0
     {
@@ -537,7 +561,7 @@ int train_forward_backward(TrCtx& c, float* loss_out, float pos_weight) {
         if ((r = tr_wgrad(c, w.dcv, 256, w.din, 96, Md, T, t->fc1.mat, t->fc1.b))) return r;
     }
     {   // cross-attention K/V projections -> gradient of the encoder memory
-        int r = tr_wgrad(c, w.dkv, 6144, mem, 512, Me, S, t->ckv.mat, t->ckv.b);
+        int r = tr_wgrad(c, w.dkv, 6144, w.xe[6], 512, Me, S, t->ckv.mat, t->ckv.b);
         if (r) return r;
         GemmParams p = tr_dgrad(c, w.dkv, 6144, 6144, Me, S, t->ckv.mat); p.out_f32 = w.dx; p.ldo = 512;
         TRL(launch_gemm_tc(p, st));
@@ -582,6 +606,13 @@ int train_forward_backward(TrCtx& c, float* loss_out, float pos_weight) {
     }
     TRL(cudaGetLastError());
     return 0;
+}
+
+int train_forward_backward(TrCtx& c, float* loss_out, float pos_weight) {
+    int r = train_forward(c);
+    if (!r) r = train_loss(c, loss_out, pos_weight);
+    if (!r) r = train_backward(c);
+    return r;
 }
 
 __global__ void set_u64_kernel(uint64_t* p, uint64_t v) { *p = v; }

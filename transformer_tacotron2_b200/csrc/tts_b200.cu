@@ -614,6 +614,31 @@ extern "C" int tts_decode_status(TtsHandle* h, void* ws, int* t_done, int* n_fin
     return 0;
 }
 
+extern "C" int tts_decode_set_frame(TtsHandle* h, void* ws, int t, const float* frames, void* stream) {
+    if (!h || !ws || !frames) return TTS_E_ARG;
+    if (!h->dec_active) FAIL(TTS_E_STATE, "tts_decode_begin not called");
+    if (t < 0 || t >= h->dec_t) FAIL(TTS_E_ARG, "frame index must lie in [0, frames decoded so far)");
+    DEV_GUARD(h);
+    const Ws L = Ws::make(h->dec_B, h->dec_S, h->dec_T);
+    CK(cudaMemcpy2DAsync(wsp<float>(ws, L.mel_before) + (size_t)t * 80, (size_t)h->dec_T * 80 * 4, frames, 80 * 4, 80 * 4, (size_t)h->dec_B,
+                         cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int tts_decode_get_frame(TtsHandle* h, void* ws, int t, float* frames, float* stop_logits, void* stream) {
+    if (!h || !ws || !frames) return TTS_E_ARG;
+    if (!h->dec_active) FAIL(TTS_E_STATE, "tts_decode_begin not called");
+    if (t < 0 || t >= h->dec_t) FAIL(TTS_E_ARG, "frame index must lie in [0, frames decoded so far)");
+    DEV_GUARD(h);
+    const Ws L = Ws::make(h->dec_B, h->dec_S, h->dec_T);
+    CK(cudaMemcpy2DAsync(frames, 80 * 4, wsp<float>(ws, L.mel_before) + (size_t)t * 80, (size_t)h->dec_T * 80 * 4, 80 * 4, (size_t)h->dec_B,
+                         cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (stop_logits)
+        CK(cudaMemcpy2DAsync(stop_logits, 4, wsp<float>(ws, L.stop_logits) + t, (size_t)h->dec_T * 4, 4, (size_t)h->dec_B, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return 0;
+}
+
 extern "C" int tts_decode_end(TtsHandle* h, void* ws, int T_out, float* mel_after, int32_t* mel_lens, float* stop_logits,
                               float* mel_before, void* stream) {
     if (!h || !ws || !mel_after || T_out <= 0) return TTS_E_ARG;
@@ -928,6 +953,58 @@ extern "C" int tts_train_step(TtsHandle* h, void* ws, const int64_t* phonemes, c
     }
     t->seen_key = key;
     return train_forward_backward(c, loss_out, pos_weight);
+}
+namespace {
+// context of one training call: workspace views, dropout threshold / scale, flat parameter and gradient buffers
+TrCtx train_ctx(TtsHandle* h, void* ws, int B, int S, int T, int utt_offset, double p_residual, cudaStream_t st) {
+    TrCtx c;
+    TtsTrain* t = h->train;
+    c.h = h; c.t = t; c.w = TrWs::make(reinterpret_cast<unsigned char*>(ws), B, S, T); c.st = st;
+    c.B = B; c.S = S; c.T = T; c.seed = c.w.seed_dev; c.utt0 = utt_offset;
+    c.thresh = (uint32_t)(p_residual * 4294967296.0); c.dscale = 1.0f / (float)(1.0 - p_residual);
+    c.P = t->P; c.G = t->G;
+    return c;
+}
+}  // namespace
+extern "C" int tts_train_forward(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* phoneme_lens, const float* mels, const int32_t* mel_lens,
+                                 int B, int S, int T, uint64_t seed, int utt_offset, double p_residual, void* stream) {
+    if (!h || !ws || !phonemes || !phoneme_lens || !mels || !mel_lens || B <= 0 || S <= 0 || T <= 0) return TTS_E_ARG;
+    if (!h->train) FAIL(TTS_E_STATE, "tts_train_begin has not been called");
+    if (S > h->cfg.max_pos || T > h->cfg.max_pos) FAIL(TTS_E_ARG, "sequence exceeds max_pos");
+    if (p_residual < 0.0 || p_residual >= 1.0) FAIL(TTS_E_ARG, "p_residual out of range");
+    DEV_GUARD(h);
+    TrCtx c = train_ctx(h, ws, B, S, T, utt_offset, p_residual, (cudaStream_t)stream);
+    CK(cudaMemcpyAsync(c.w.plens, phoneme_lens, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
+    CK(cudaMemcpyAsync(c.w.mlens, mel_lens, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
+    CK(cudaMemcpyAsync(c.w.ph_in, phonemes, (size_t)B * S * 8, cudaMemcpyDeviceToDevice, c.st));
+    CK(cudaMemcpyAsync(c.w.mels_in, mels, (size_t)B * T * 80 * 4, cudaMemcpyDeviceToDevice, c.st));
+    set_u64_kernel<<<1, 1, 0, c.st>>>(c.w.seed_dev, seed);
+    ++launch_counter();
+    return train_forward(c);
+}
+extern "C" int tts_train_backward(TtsHandle* h, void* ws, int B, int S, int T, int utt_offset, double p_residual, const float* d_before,
+                                  const float* d_after, const float* d_stop, void* stream) {
+    if (!h || !ws || !d_before || !d_after || !d_stop || B <= 0 || S <= 0 || T <= 0) return TTS_E_ARG;
+    if (!h->train) FAIL(TTS_E_STATE, "tts_train_begin has not been called");
+    if (p_residual < 0.0 || p_residual >= 1.0) FAIL(TTS_E_ARG, "p_residual out of range");
+    DEV_GUARD(h);
+    TrCtx c = train_ctx(h, ws, B, S, T, utt_offset, p_residual, (cudaStream_t)stream);      // (the seed staged by the forward is still in the workspace)
+    const size_t n = (size_t)B * T;
+    CK(cudaMemcpyAsync(c.w.dbefore, d_before, n * 80 * 4, cudaMemcpyDeviceToDevice, c.st));
+    CK(cudaMemcpyAsync(c.w.dafter, d_after, n * 80 * 4, cudaMemcpyDeviceToDevice, c.st));
+    CK(cudaMemcpyAsync(c.w.dstop, d_stop, n * 4, cudaMemcpyDeviceToDevice, c.st));
+    return train_backward(c);
+}
+extern "C" int tts_train_write(TtsHandle* h, int which, int64_t offset, int64_t numel, const float* host_in) {
+    if (!h || !h->train || !host_in || offset < 0 || numel <= 0) return TTS_E_ARG;
+    TtsTrain* t = h->train;
+    float* dst = which == 0 ? t->P : which == 2 ? t->RS : nullptr;
+    const size_t lim = which == 2 ? t->nrs : t->n;
+    if (!dst || (size_t)(offset + numel) > lim) return TTS_E_ARG;
+    DEV_GUARD(h);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(dst + offset, host_in, (size_t)numel * 4, cudaMemcpyHostToDevice));
+    return 0;
 }
 extern "C" int tts_train_outputs(TtsHandle* h, void* ws, int B, int S, int T, float* mel_before, float* mel_after, float* stop_logits, void* stream) {
     if (!h || !ws || !h->train) return TTS_E_ARG;

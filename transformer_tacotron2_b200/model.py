@@ -107,6 +107,32 @@ class _Stack(nn.Module):
         self.layers = nn.ModuleList(layers)
 
 
+class _TrainForwardFn(torch.autograd.Function):
+    """model.train(); out = model(...); loss(out).backward(): the library's train-mode forward and backward behind autograd.
+    The module's parameters ride along as inputs so that autograd routes the flat gradient buffer back to them."""
+
+    @staticmethod
+    def forward(ctx, model, trainer, phonemes, phoneme_lens, mels, mel_lens, seed, utt_offset, *params):
+        mb, ma, st = trainer.forward_only(phonemes, phoneme_lens, mels, mel_lens, seed, utt_offset)
+        ctx.model, ctx.trainer = model, trainer
+        ctx.names = [n for n, _ in model.named_parameters()]
+        ctx.pinfo = [(p.shape, p.device, p.dtype) for p in params]
+        T = mels.shape[1]
+        ctx.mask = (torch.arange(T, device=mb.device)[None, :] < mel_lens.to(mb.device)[:, None]).to(torch.float32)
+        return mb, ma, st
+
+    @staticmethod
+    def backward(ctx, g_mb, g_ma, g_st):
+        tr = ctx.trainer
+        mask = ctx.mask
+        z = lambda g, ref: torch.zeros(ref, device=mask.device) if g is None else g                      # noqa: E731
+        B, T = mask.shape
+        tr.backward_from(z(g_mb, (B, T, 80)) * mask[..., None], z(g_ma, (B, T, 80)) * mask[..., None], z(g_st, (B, T)) * mask)
+        grads = tr.grads()                                                                               # name -> host tensor
+        out = [grads[n].to(dev, dt).view(shape) for n, (shape, dev, dt) in zip(ctx.names, ctx.pinfo)]
+        return (None,) * 8 + tuple(out)
+
+
 class TransformerTTS(nn.Module):
     """forward(): teacher-forced (eval-mode arithmetic); inference(): greedy AR over a KV cache.
 
@@ -131,6 +157,8 @@ class TransformerTTS(nn.Module):
         self._dirty = True
         self._host_stale = False         # a Trainer has stepped the device-side parameters; the module's copies are behind
         self._trainer = None             # weakref to the Trainer that owns the training state (training.py)
+        self._ag_trainer = None          # Trainer behind the autograd bridge (train-mode forward), created on first use
+        self._ag_version = None
         self._synced_version = None
         self.profile_events = False      # bench.py: CUDA-event time of the decode loop per inference()
         self.decode_ms = []
@@ -239,14 +267,16 @@ class TransformerTTS(nn.Module):
         return ids[0]
 
     # ------------------------------------------------------------------ teacher-forced
-    @torch.no_grad()
     def forward(self, phonemes, phoneme_lens, mels, mel_lens, seed: int = 0, utt_ids=None, utt_offset: int = 0
                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """phonemes [B,S] i64, phoneme_lens [B], mels [B,T,80] f32, mel_lens [B]
         -> mel_before [B,T,80], mel_after [B,T,80], stop_logits [B,T]  (on the GPU, zero past mel_lens)."""
         if self.training:
-            raise NotImplementedError("train-mode steps go through transformer_tacotron2_b200.training.Trainer (forward + loss + backward in the library); "
-                                      "this method is the eval-mode forward")
+            return self._train_forward(phonemes, phoneme_lens, mels, mel_lens, seed, self._utt_offset(utt_ids, phonemes.shape[0], utt_offset))
+        with torch.no_grad():
+            return self._eval_forward(phonemes, phoneme_lens, mels, mel_lens, seed, utt_ids, utt_offset)
+
+    def _eval_forward(self, phonemes, phoneme_lens, mels, mel_lens, seed, utt_ids, utt_offset):
         lib = self._ensure_handle()
         self.sync_weights()
         dev = self.device
@@ -262,6 +292,30 @@ class TransformerTTS(nn.Module):
                              int(seed), self._utt_offset(utt_ids, B, utt_offset), mb.data_ptr(), ma.data_ptr(), st.data_ptr(), self._stream())
         self._check(rc, "tts_forward")
         return mb, ma, st
+
+    def _train_forward(self, phonemes, phoneme_lens, mels, mel_lens, seed, utt_offset):
+        """Train-mode forward with autograd: `model.train(); out = model(...); loss_fn(*out).backward(); optimiser.step()` works on
+        the module exactly as on the oracle (oracle/transformer_tts.py: forward in .train() mode).  Arithmetic: the library's
+        training forward / backward (tts_train_forward / tts_train_backward); gradients are copied into the (host) parameters'
+        .grad.  This is the compatibility path -- transformer_tacotron2_b200.training.Trainer keeps parameters, gradients and
+        the optimiser on the device and is the fast one."""
+        from .training import Trainer
+        with torch.no_grad():
+            tr = self._ag_trainer
+            if tr is None:
+                tr = self._ag_trainer = Trainer(self)
+                self._ag_version = self._param_version()
+            elif self._ag_version != self._param_version():          # an optimiser (or the user) changed the module's tensors
+                tr.write_parameters(self._raw_state_dict())
+                self._ag_version = self._param_version()
+        out = _TrainForwardFn.apply(self, tr, phonemes, phoneme_lens, mels, mel_lens, int(seed), int(utt_offset), *list(self.parameters()))
+        with torch.no_grad():                                        # BatchNorm running statistics moved in the forward: mirror them
+            sd = self._raw_state_dict()
+            for k, v in tr.buffers().items():
+                sd[k].copy_(v)
+            self._ag_version = self._param_version()
+            self._dirty = True                                       # the packed inference weights fold the old statistics
+        return out
 
     # ------------------------------------------------------------------ greedy AR
     @torch.no_grad()

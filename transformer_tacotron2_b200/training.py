@@ -108,6 +108,44 @@ class Trainer:
         self._shape = (B, S, T)
         return self._loss
 
+    # ------------------------------------------------------------------ autograd bridge (model.train(); model(...); loss.backward())
+    def forward_only(self, phonemes, phoneme_lens, mels, mel_lens, seed: int = 0, utt_offset: int = 0):
+        """Train-mode forward alone; the activations stay in the workspace for backward_from().  -> (mel_before, mel_after, stop)."""
+        m, dev = self.model, self.model.device
+        B, S = phonemes.shape
+        T = mels.shape[1]
+        self._in = (phonemes.to(dev, torch.int64).contiguous(), phoneme_lens.to(dev, torch.int32).contiguous(),
+                    mels.to(dev, torch.float32).contiguous(), mel_lens.to(dev, torch.int32).contiguous())
+        ph, pl, me, ml = self._in
+        ws = self._workspace(B, S, T)
+        rc = self._lib.tts_train_forward(self._h, ws.data_ptr(), ph.data_ptr(), pl.data_ptr(), me.data_ptr(), ml.data_ptr(), B, S, T, int(seed),
+                                         int(utt_offset), self.p_residual, m._stream())
+        m._check(rc, "tts_train_forward")
+        self._shape = (B, S, T)
+        self._fwd_args = (int(utt_offset),)
+        return self.outputs()
+
+    def backward_from(self, d_before, d_after, d_stop):
+        """Back-propagate dLoss/d(mel_before), dLoss/d(mel_after), dLoss/d(stop_logits) of any loss through the last forward_only();
+        the parameter gradients land in flat_grads."""
+        m, dev = self.model, self.model.device
+        B, S, T = self._shape
+        g = [t.to(dev, torch.float32).contiguous() for t in (d_before, d_after, d_stop)]
+        rc = self._lib.tts_train_backward(self._h, self._ws.data_ptr(), B, S, T, self._fwd_args[0], self.p_residual,
+                                          g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), m._stream())
+        m._check(rc, "tts_train_backward")
+        torch.cuda.current_stream(dev).synchronize()           # g[] must outlive the copies
+
+    def write_parameters(self, state: Dict[str, torch.Tensor]):
+        """Overwrite the device-side parameters / BatchNorm statistics from host tensors keyed like state_dict(), then refresh the
+        bf16 operand copies (the autograd bridge calls this after a torch optimiser stepped the module's parameters)."""
+        flat_p, flat_b = None, None
+        for name, off, numel, isb in self._table:
+            t = state[name].detach().to("cpu", torch.float32).contiguous().view(-1)
+            assert t.numel() == numel, name
+            self.model._check(self._lib.tts_train_write(self._h, 2 if isb else 0, off, numel, C.c_void_p(t.data_ptr())), "tts_train_write")
+        self.model._check(self._lib.tts_train_repack(self._h, self.model._stream()), "tts_train_repack")
+
     def all_reduce_grads(self):
         if self.world_size > 1:
             allreduce_sum_(self.flat_grads, self.group)

@@ -107,6 +107,16 @@ int tts_forward(TtsHandle* h, void* ws, const int64_t* phonemes, const int32_t* 
                 const float* mels, const int32_t* mel_lens, int B, int S, int T, uint64_t seed, int utt_offset,
                 float* mel_before, float* mel_after, float* stop_logits, void* stream);
 
+/* Optional per-utterance controls of a decode session (between tts_decode_begin and the first tts_decode_steps; device int32 [B],
+ * either may be NULL):
+ *   utt_ids   global utterance id of every row = its dropout key (default utt_offset + row).  With ids the batch may be decoded in
+ *             ANY order -- e.g. sorted by length so that the utterances of a cluster group stop together -- with bit-identical
+ *             per-utterance results;
+ *   max_lens  per-utterance frame budget <= max_len: the utterance also stops (length = budget) when it is used up;
+ *   work_stealing != 0: the clusters draw their utterance groups from a device-side queue instead of a static round-robin, so a
+ *             cluster whose group has stopped immediately starts the next one (8(f)-3: continuous batching at group granularity). */
+int tts_decode_set_batch(TtsHandle* h, void* ws, const int32_t* utt_ids, const int32_t* max_lens, int work_stealing, void* stream);
+
 /* Forced ("step-locked") decoding: overwrite frame t (< frames decoded so far) of the session's mel_before buffer with
  * frames [B][80] fp32 (device memory).  The next tts_decode_steps() call resumes from frame t_done - 1, so writing frame
  * t_done - 1 between single-step calls feeds the decoder somebody else's trajectory (the parity tests feed the oracle's). */

@@ -36,6 +36,7 @@ SIGNATURES = {
     "tts_decode_steps": (_I, [_P, _P, _I, _P]),
     "tts_decode_status": (_I, [_P, _P, C.POINTER(_I), C.POINTER(_I), _P]),
     "tts_decode_end": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
+    "tts_decode_set_batch": (_I, [_P, _P, _P, _P, _I, _P]),
     "tts_decode_set_frame": (_I, [_P, _P, _I, _P, _P]),
     "tts_decode_get_frame": (_I, [_P, _P, _I, _P, _P, _P]),
     "tts_infer_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _U64, _I, _P, _P, _P, C.POINTER(_I), _P]),

@@ -72,7 +72,7 @@ constexpr int SM_H2 = SM_ABUF;                                  // aliases abuf 
 constexpr int SM_FBUF = SM_H1 + CL_G * 528;                     // bf16 [G][136] previous frame (K padded to 128)
 constexpr int SM_AMERGE = SM_FBUF + CL_G * 272;                 // f32 [16][68]  attention partials (m, l, o[64]) per warp
 constexpr int SM_MISC = SM_AMERGE + 4352;                       // mbarriers + flags + head records + group lengths
-constexpr int CL_SMEM_BYTES = SM_MISC + 384;                    // 17 mbarriers (136 B) | flags @192 | hrec @224 | glens @352
+constexpr int CL_SMEM_BYTES = SM_MISC + 448;                    // 17 mbarriers (136 B) | flags @192 | hrec @224 | glens @352 | guids @384 | gtlens @416
 static_assert(CL_SMEM_BYTES <= 232448, "decode kernel shared memory exceeds 227 KB");
 // (MMA B fragments are loaded with ldmatrix over 8 rows: rows >= G read whatever follows the buffer -- finite or not, they
 //  only feed output columns m >= G, which are never used.)
@@ -91,6 +91,10 @@ struct ClusterParams {
     bf16* self_kv;                               // [6][B][8][nblk_self][KV_BLOCK_ELEMS]
     const bf16* cross_kv;                        // [6][B][8][nblk_cross][KV_BLOCK_ELEMS]
     const int* plens;
+    const int* utt_ids;                          // optional [B]: global utterance id of every row (dropout key); null -> utt_offset + b
+    const int* tlens;                            // optional [B]: per-utterance frame budget (an utterance also stops at tlens[b]); null -> Tmax
+    int* group_queue;                            // optional device counter: clusters draw their next utterance group from it (work
+                                                 // stealing: a cluster whose group has stopped takes the next one); null -> static round-robin
     float* mel_before; float* stop_logits; int* lens; int* finished; int* n_finished;
     unsigned long long* ts;                      // optional [Tmax][CL_TS_COLS] %globaltimer stamps (cluster 0, rank 0)
     int dbg_rank;
@@ -587,6 +591,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
     volatile int* flags = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 192);
     volatile int* hrec = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 192 + 32);             // [8 ranks][4]
     volatile int* glens = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 192 + 32 + 128);      // [CL_G]
+    volatile int* guids = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 384);                 // [CL_G] global utterance ids (dropout key)
+    volatile int* gtlens = reinterpret_cast<volatile int*>(cl_smem + SM_MISC + 416);                // [CL_G] frame budgets; [7] = next group (queue mode)
     c.rank = (int)cluster_ctarank();
     c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
     const int cid = (int)cluster_id_x(), ncl = (int)cluster_nid_x();
@@ -626,7 +632,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
         }
     };
 
-    for (int grp = cid; grp < p.ngroups; grp += ncl) {
+    for (int grp = cid;; grp += ncl) {
+        if (p.group_queue != nullptr) {                  // work stealing: CTA 0 draws the cluster's next group and tells its peers
+            if (c.rank == 0 && c.tid == 0) {
+                const int gq = atomicAdd(p.group_queue, 1);
+                for (int r = 0; r < CL_SIZE; ++r)
+                    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(map_to_rank(smem_u32(const_cast<int*>(gtlens) + 7), (uint32_t)r)), "r"(gq) : "memory");
+            }
+            hw_cluster_sync();
+            grp = gtlens[7];
+        }
+        if (grp >= p.ngroups) break;
         c.b0 = grp * p.G; c.G = min(p.G, p.B - c.b0);
         // ---- (re)initialise the ring and the activation buffers
         if (!is_producer)
@@ -639,7 +655,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
             mbar_expect_tx(&c.gsync[0], gather_bytes(0, c.G));          // phases 0 and 1 are armed before the start barrier
             mbar_expect_tx(&c.gsync[1], gather_bytes(1, c.G));
             int nf = 0;
-            for (int m = 0; m < c.G; ++m) { nf += p.finished[c.b0 + m]; glens[m] = p.plens[c.b0 + m]; }
+            for (int m = 0; m < c.G; ++m) {
+                nf += p.finished[c.b0 + m]; glens[m] = p.plens[c.b0 + m];
+                guids[m] = p.utt_ids ? p.utt_ids[c.b0 + m] : p.utt_offset + c.b0 + m;
+                gtlens[m] = p.tlens ? min(p.Tmax, p.tlens[c.b0 + m]) : p.Tmax;
+            }
             flags[0] = nf; flags[1] = 0; flags[2] = 0;
         }
         __syncthreads();
@@ -669,7 +689,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         [&](int ti, int n, int m, float v) {
                             const int col = c.rank * 32 + ti * 16 + n;
                             v = fmaxf(v, 0.f);
-                            wst[m * 16 + n] = keep_bit(p.seed, SITE_DEC_PRENET_FC1, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
+                            wst[m * 16 + n] = keep_bit(p.seed, SITE_DEC_PRENET_FC1, (uint32_t)t, (uint32_t)guids[m], (uint32_t)col) ? 2.f * v : 0.f;
                         });
                 if (c.warp < 2) { __syncwarp(); push_tile_bf16(c, wst, h1 + c.rank * 32 + c.warp * 16, LDX256); }
                 gather_sync(c);
@@ -679,7 +699,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         [&](int ti, int n, int m, float v) {
                             const int col = c.rank * 32 + ti * 16 + n;
                             v = fmaxf(v, 0.f);
-                            wst[m * 16 + n] = keep_bit(p.seed, SITE_DEC_PRENET_FC2, (uint32_t)t, (uint32_t)(p.utt_offset + c.b0 + m), (uint32_t)col) ? 2.f * v : 0.f;
+                            wst[m * 16 + n] = keep_bit(p.seed, SITE_DEC_PRENET_FC2, (uint32_t)t, (uint32_t)guids[m], (uint32_t)col) ? 2.f * v : 0.f;
                         });
                 if (c.warp < 2) { __syncwarp(); push_tile_bf16(c, wst, h2 + c.rank * 32 + c.warp * 16, LDX256); }
                 gather_sync(c);
@@ -826,7 +846,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                                 if (col < 80) p.mel_before[((size_t)b * p.Tmax + t) * 80 + col] = v;   // fp32 feedback (P8)
                                 else if (col == 80) {
                                     p.stop_logits[(size_t)b * p.Tmax + t] = v;
-                                    if (v > 0.f && p.finished[b] == 0) {                         // P10
+                                    if ((v > 0.f || t + 1 >= gtlens[m]) && p.finished[b] == 0) { // P10 (or the utterance's frame budget is used up)
                                         p.finished[b] = 1; p.lens[b] = t + 1; atomicAdd(p.n_finished, 1);
                                         atomicAdd(const_cast<int*>(flags), 1);                   // rank 5 keeps the group's count
                                     }

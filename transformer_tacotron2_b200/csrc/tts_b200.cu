@@ -54,6 +54,7 @@ struct TtsHandle {
     bf16* post_w[5] = {}; float* post_b[5] = {};
     float* pe = nullptr;
     // ---- decode session
+    bool dec_ids = false, dec_tlens = false, dec_steal = false;       // tts_decode_set_batch
     bool dec_active = false; int dec_B = 0, dec_S = 0, dec_T = 0, dec_t = 0; uint64_t dec_seed = 0; int dec_utt0 = 0;
     int* h_status = nullptr;                                          // pinned: t_done, n_finished
     TtsTrain* train = nullptr;                                        // training state (train.cuh), built by tts_train_begin
@@ -84,7 +85,7 @@ static inline uint16_t f2bf(float f) {                                // round-t
 // Workspace layout
 struct Ws {
     size_t total = 0;
-    size_t self_kv, cross_kv, mel_before, stop_logits, lens, finished, scalars, ts;
+    size_t self_kv, cross_kv, mel_before, stop_logits, lens, finished, scalars, ts, utt_ids, tlens;
     size_t x, x2, wide, a, y, mel16, mel32, ph, plens, mlens;         // sequence-parallel activations
     int Tpad, Spad, nblk_self, nblk_cross;
     size_t self_kv_bytes, cross_kv_bytes;
@@ -103,7 +104,8 @@ struct Ws {
         w.cross_kv = take(w.cross_kv_bytes);
         w.mel_before = take((size_t)B * T * 80 * 4);
         w.stop_logits = take((size_t)B * T * 4);
-        w.lens = take(B * 4); w.finished = take(B * 4); w.scalars = take(64);
+        w.lens = take(B * 4); w.finished = take(B * 4); w.scalars = take(64);          // scalars: [0] n_finished, [1] group queue
+        w.utt_ids = take(B * 4); w.tlens = take(B * 4);
         w.ts = take((size_t)(T + 1) * CL_TS_COLS * 8);
         w.x = take(M * 512 * 2); w.x2 = take(M * 512 * 2); w.wide = take(M * 2048 * 2); w.a = take(M * 512 * 2);
         w.y = take(M * 512 * 4); w.mel16 = take(M * 96 * 2); w.mel32 = take(M * 80 * 4);
@@ -530,6 +532,7 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
     DEV_GUARD(h);
     cudaStream_t st = (cudaStream_t)stream;
     const Ws L = Ws::make(B, S, max_len);
+    h->dec_ids = h->dec_tlens = h->dec_steal = false;
     h->dec_active = true; h->dec_B = B; h->dec_S = S; h->dec_T = max_len; h->dec_t = 0; h->dec_seed = seed; h->dec_utt0 = utt_offset;
     init_decode_state_kernel<<<(std::max(B, 4) + 255) / 256, 256, 0, st>>>(wsp<int>(ws, L.lens), wsp<int>(ws, L.finished),
                                                                           wsp<int>(ws, L.scalars), B, max_len);
@@ -586,6 +589,13 @@ extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* strea
     cfg.attrs = at; cfg.numAttrs = 1;
     h->cparams.ts = h->decode_timestamps ? wsp<unsigned long long>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).ts) : nullptr;
     // (the debug dump lands in the `wide` activation buffer, idle during the decode loop: >= B * 2048 * 2 bytes per row of S/T)
+    {
+        const Ws L = Ws::make(h->dec_B, h->dec_S, h->dec_T);
+        h->cparams.utt_ids = h->dec_ids ? wsp<int>(ws, L.utt_ids) : nullptr;
+        h->cparams.tlens = h->dec_tlens ? wsp<int>(ws, L.tlens) : nullptr;
+        h->cparams.group_queue = h->dec_steal ? wsp<int>(ws, L.scalars) + 1 : nullptr;
+        if (h->dec_steal) CK(cudaMemsetAsync(wsp<int>(ws, L.scalars) + 1, 0, 4, st));
+    }
     h->cparams.dbg_rank = h->decode_debug - 1;
     h->cparams.dbg = h->decode_debug ? wsp<float>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).wide) : nullptr;
     CK(cudaLaunchKernelEx(&cfg, decode_cluster_kernel, h->cparams, h->dec_t, n_steps));
@@ -611,6 +621,18 @@ extern "C" int tts_decode_status(TtsHandle* h, void* ws, int* t_done, int* n_fin
     }
     if (n_finished) *n_finished = nf;
     if (t_done) *t_done = h->dec_t;
+    return 0;
+}
+
+extern "C" int tts_decode_set_batch(TtsHandle* h, void* ws, const int32_t* utt_ids, const int32_t* max_lens, int work_stealing, void* stream) {
+    if (!h || !ws) return TTS_E_ARG;
+    if (!h->dec_active || h->dec_t != 0) FAIL(TTS_E_STATE, "tts_decode_set_batch belongs between tts_decode_begin and the first tts_decode_steps");
+    DEV_GUARD(h);
+    const Ws L = Ws::make(h->dec_B, h->dec_S, h->dec_T);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (utt_ids) CK(cudaMemcpyAsync(wsp<int>(ws, L.utt_ids), utt_ids, (size_t)h->dec_B * 4, cudaMemcpyDeviceToDevice, st));
+    if (max_lens) CK(cudaMemcpyAsync(wsp<int>(ws, L.tlens), max_lens, (size_t)h->dec_B * 4, cudaMemcpyDeviceToDevice, st));
+    h->dec_ids = utt_ids != nullptr; h->dec_tlens = max_lens != nullptr; h->dec_steal = work_stealing != 0;
     return 0;
 }
 

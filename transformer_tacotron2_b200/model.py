@@ -320,7 +320,8 @@ class TransformerTTS(nn.Module):
     # ------------------------------------------------------------------ greedy AR
     @torch.no_grad()
     def inference(self, phonemes, phoneme_lens, max_len: int = 800, seed: int = 0, utt_ids=None, utt_offset: int = 0,
-                  return_before: bool = False, clone_outputs: bool = True):
+                  return_before: bool = False, clone_outputs: bool = True, max_lens=None, sort_by_length: bool = False,
+                  work_stealing: Optional[bool] = None):
         """-> mel_after [B,Tout,80], mel_lens [B] i32, stop_logits [B,Tout].
 
         CPU tensors in -> the whole call runs through tts_infer_host (H2D, encoder, decode loop,
@@ -329,13 +330,26 @@ class TransformerTTS(nn.Module):
 
         Host path: results are read back into pinned staging buffers the module keeps per (B, max_len).  With
         clone_outputs=True (default) private copies are returned; clone_outputs=False returns views of the staging buffers,
-        valid until the next host-path call with the same shape (serving loops that consume the mel right away)."""
+        valid until the next host-path call with the same shape (serving loops that consume the mel right away).
+
+        Ragged batches: `utt_ids` may be ANY ids (they key the dropout masks, so an utterance's result does
+        not depend on its position in the batch); `max_lens` [B] gives every utterance its own frame budget (it stops there at
+        the latest); `sort_by_length=True` decodes the batch sorted by budget / phoneme length, so that the utterances sharing
+        a cluster group stop together, and returns the results in the caller's order -- bit-identical to the unsorted call;
+        `work_stealing` lets a cluster whose group has stopped take the next group from a device-side queue (default: on
+        whenever max_lens or sort_by_length is used)."""
         lib = self._ensure_handle()
         self.sync_weights()
         B, S = phonemes.shape
-        u0 = self._utt_offset(utt_ids, B, utt_offset)
+        ids = None
+        if utt_ids is not None:
+            ids = torch.as_tensor([int(v) for v in utt_ids], dtype=torch.int32)
+            if ids.tolist() == list(range(int(ids[0]), int(ids[0]) + B)):
+                utt_offset, ids = int(ids[0]), None                    # a contiguous range is just an offset
+        u0 = int(utt_offset)
+        ragged = ids is not None or max_lens is not None or sort_by_length
         ws = self._workspace(B, S, max_len)
-        if not phonemes.is_cuda and not return_before:
+        if not phonemes.is_cuda and not return_before and not ragged:
             ph = phonemes.to(torch.int64).contiguous()
             pl = phoneme_lens.to(torch.int32).contiguous()
             key = (B, int(max_len))
@@ -352,10 +366,27 @@ class TransformerTTS(nn.Module):
             out = (ma.view(-1)[: B * T * 80].view(B, T, 80), ml, st.view(-1)[: B * T].view(B, T))
             return tuple(t.clone() for t in out) if clone_outputs else out
         dev = self.device
+        to_host = not phonemes.is_cuda
         ph = phonemes.to(dev, torch.int64).contiguous()
         pl = phoneme_lens.to(dev, torch.int32).contiguous()
+        perm = inv = None
+        mlens_d = None if max_lens is None else torch.as_tensor(max_lens).to(dev, torch.int32).clamp(1, int(max_len)).contiguous()
+        ids_d = None if ids is None else ids.to(dev)
+        if sort_by_length:
+            keyv = (mlens_d if mlens_d is not None else pl).to(torch.int64)
+            perm = torch.argsort(keyv, descending=True, stable=True)
+            inv = torch.empty_like(perm); inv[perm] = torch.arange(B, device=dev)
+            if ids_d is None:
+                ids_d = torch.arange(u0, u0 + B, device=dev, dtype=torch.int32)
+            ph, pl, ids_d = ph[perm].contiguous(), pl[perm].contiguous(), ids_d[perm].contiguous()
+            if mlens_d is not None:
+                mlens_d = mlens_d[perm].contiguous()
         stream = self._stream()
         self._check(lib.tts_decode_begin(self._handle, ws.data_ptr(), B, S, int(max_len), int(seed), u0, stream), "tts_decode_begin")
+        if ragged:
+            steal = ragged if work_stealing is None else bool(work_stealing)
+            self._check(lib.tts_decode_set_batch(self._handle, ws.data_ptr(), ids_d.data_ptr() if ids_d is not None else None,
+                                                 mlens_d.data_ptr() if mlens_d is not None else None, int(steal), stream), "tts_decode_set_batch")
         self._check(lib.tts_encode(self._handle, ws.data_ptr(), ph.data_ptr(), pl.data_ptr(), B, S, int(max_len), None, stream), "tts_encode")
         td, nf = C.c_int(0), C.c_int(0)
         chunk = int(max_len)                               # one launch: every cluster stops itself on the device
@@ -378,9 +409,12 @@ class TransformerTTS(nn.Module):
         rc = lib.tts_decode_end(self._handle, ws.data_ptr(), T, ma.data_ptr(), ml.data_ptr(), st.data_ptr(),
                                 mb.data_ptr() if return_before else None, stream)
         self._check(rc, "tts_decode_end")
-        if return_before:
-            return ma, ml, st, mb
-        return ma, ml, st
+        out = (ma, ml, st, mb) if return_before else (ma, ml, st)
+        if inv is not None:
+            out = tuple(t[inv] for t in out)
+        if to_host:
+            out = tuple(t.cpu() for t in out)
+        return out
 
     def phase_timestamps(self, n_steps: int) -> torch.Tensor:
         """[n_steps, n_phases] int64 ns stamps of the last persistent decode (option decode_timestamps = 1)."""

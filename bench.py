@@ -312,6 +312,32 @@ def run_b200(args, rank, world, local_rank):
         ms, dms = measure_case("long", 16, 300, 1600, rank * 16, 2, "")
         extra["long"] = case_line("configs[4]: long-utterance inference, B=16/GPU, S=300, 1600 frames", 16, 300, 1600, world, ms, dms)
 
+    if not args.no_extra:
+        # a ragged batch (256 utterances per GPU, frame budgets U[0.6, 1] x T) -- valid frames / s with the
+        # batch decoded in the caller's order on statically assigned clusters, and sorted by length with clusters stealing groups
+        Br = 256
+        phr, plr = synthetic_inputs(Br, S, DATA_SEED + 29)
+        phr, plr = phr.to(dev), plr.to(dev)
+        gen = torch.Generator().manual_seed(DATA_SEED + 31 + rank)
+        budgets = (T * (0.6 + 0.4 * torch.rand(Br, generator=gen))).to(torch.int32).clamp(1, T).to(dev)
+        valid = int(budgets.sum())
+        res = {}
+        for name, kw in (("unsorted_static", dict(sort_by_length=False, work_stealing=False)), ("sorted_stealing", dict(sort_by_length=True, work_stealing=True))):
+            for _ in range(2):
+                o = model.inference(phr, plr, max_len=T, seed=DROPOUT_SEED, utt_offset=rank * Br, max_lens=budgets, **kw)
+            assert o[1].tolist() == budgets.tolist()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(2):
+                model.inference(phr, plr, max_len=T, seed=DROPOUT_SEED, utt_offset=rank * Br, max_lens=budgets, **kw)
+            b.record()
+            barrier()
+            res[name] = world * valid / (max_over_ranks(a.elapsed_time(b)) / 2 * 1e-3)
+        extra["ragged"] = {"value": res["sorted_stealing"], "unit": "valid frames/s", "unsorted_static": res["unsorted_static"],
+                           "config": {"workload": f"ragged batch: {Br} utterances/GPU, S={S}, frame budgets U[0.6,1] x {T} (mean {valid / Br:.0f}), "
+                                                  "length-sorted groups + device-side group queue vs caller order + static clusters"}}
+
     # ---- second half of BASELINE.json's metric: teacher-forced train step (configs[3]: B = 32 per GPU, data parallel,
     #      one NCCL all-reduce over the flat gradient buffer per step), utterances / s over all ranks -------------------
     train = None

@@ -419,6 +419,21 @@ def run_b200(args, rank, world, local_rank):
         threads = os.cpu_count() or 1
         v, desc = cpu_oracle_sample(B, S, T, window=args.cpu_window, threads=threads)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc}
+        if not args.no_cpu_full_b1:
+            # how good is the sampled estimate?  configs[1] (batch 1, 800 frames) is short enough to run IN FULL on the CPU:
+            # time it, and put the affine 3-window estimate of the same workload beside it
+            from oracle import TransformerTTS as Oracle
+            torch.set_num_threads(threads)
+            o = Oracle().eval(); o.load_state_dict(synthetic_state_dict().state_dict())
+            ph1, pl1 = synthetic_inputs(1, S, DATA_SEED)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                o1 = o.inference(ph1, pl1, max_len=T, seed=DROPOUT_SEED)
+            full_s = time.perf_counter() - t0
+            est_v, _ = cpu_oracle_sample(1, S, T, window=args.cpu_window, threads=threads)
+            line["cpu_baseline"]["full_run_b1"] = {"frames_per_s": T / full_s, "seconds": full_s, "frames": int(o1[1][0]),
+                                                   "sampled_estimate_frames_per_s": est_v, "estimate_over_full": est_v / (T / full_s),
+                                                   "note": "configs[1] run in full on the host cores (oracle, fp32) next to the 3-window affine estimate of the same workload"}
     print(json.dumps(line), flush=True)
 
 
@@ -435,6 +450,7 @@ def main():
     ap.add_argument("--cpu-window", type=int, default=50)
     ap.add_argument("--ref-window", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-full-b1", action="store_true", help="skip the full CPU run of configs[1] that validates the sampled estimate")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step measurement (the `train` key)")
     ap.add_argument("--train-batch", type=int, default=32)
     ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling / batch-1 latency / long-utterance lines")

@@ -61,7 +61,7 @@ constexpr size_t CLW_RANK_BYTES = (size_t)CLW_FC1 + CLW_FC2 + CLW_PROJ + 6 * (si
 constexpr int SM_RING = 0;
 constexpr int SM_XRES = SM_RING + CL_STAGES * CL_STAGE_BYTES;   // f32 [G][512]  residual stream
 constexpr int SM_YBUF = SM_XRES + CL_G * 2048;                  // f32 [G][512]  gathered pre-LN sums / FFN2 partial sums
-constexpr int SM_RECV = SM_YBUF + CL_G * 2048;                  // f32 [8 ranks][G][64] FFN2 reduce-scatter; per-warp epilogue staging otherwise
+constexpr int SM_RECV = SM_YBUF + CL_G * 2048;                  // f32 [8 ranks][G][64] FFN2 reduce-scatter
 constexpr int SM_RED = SM_RECV + CL_G * 2048;                   // [0, 4096): attention output staging; [4096, 8192): LayerNorm gamma | beta
 constexpr int SM_XA = SM_RED + 8192;                            // bf16 [G][520] LN output as MMA operand
 constexpr int SM_ABUF = SM_XA + CL_G * 1040;                    // bf16 [G][520] gathered attention outputs (prenet: h2 [G][264])
@@ -71,7 +71,8 @@ constexpr int SM_H1 = SM_HBUF + CL_G * 528;                     // bf16 [G][264]
 constexpr int SM_H2 = SM_ABUF;                                  // aliases abuf (idle during the prenet)
 constexpr int SM_FBUF = SM_H1 + CL_G * 528;                     // bf16 [G][136] previous frame (K padded to 128)
 constexpr int SM_AMERGE = SM_FBUF + CL_G * 272;                 // f32 [16][68]  attention partials (m, l, o[64]) per warp
-constexpr int SM_MISC = SM_AMERGE + 4352;                       // mbarriers + flags + head records + group lengths
+constexpr int SM_WST = SM_AMERGE + 4352;                        // f32 [4 warps][G][16] epilogue tiles of the narrow GEMMs before their push
+constexpr int SM_MISC = SM_WST + 4 * CL_G * 64;                 // mbarriers + flags + head records + group lengths
 constexpr int CL_SMEM_BYTES = SM_MISC + 448;                    // 17 mbarriers (136 B) | flags @192 | hrec @224 | glens @352 | guids @384 | gtlens @416
 static_assert(CL_SMEM_BYTES <= 232448, "decode kernel shared memory exceeds 227 KB");
 // (MMA B fragments are loaded with ldmatrix over 8 rows: rows >= G read whatever follows the buffer -- finite or not, they
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
     bf16* h1 = reinterpret_cast<bf16*>(cl_smem + SM_H1);
     bf16* h2 = reinterpret_cast<bf16*>(cl_smem + SM_H2);
     bf16* fbuf = reinterpret_cast<bf16*>(cl_smem + SM_FBUF);
-    float* wst = recv + (c.warp & 15) * (CL_G * 16);     // this warp's private epilogue tile [G][16] (recv is free outside the FFN2 exchange)
+    float* wst = reinterpret_cast<float*>(cl_smem + SM_WST) + (c.warp & 3) * (CL_G * 16);    // private epilogue tile [G][16] of warps 0..3 (the narrow GEMMs)
     const bool stamper = p.ts != nullptr && cid == 0 && c.rank == 0 && c.tid == 0;
     auto stamp = [&](int t, int idx) {
         if (stamper) {
@@ -788,20 +789,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                             [&](int ti, int n, int m, float v) { ybuf[m * 512 + ti * 16 + n] = v; },
                             (stamper && l == 0) ? p.ts + (size_t)t * CL_TS_COLS + 79 : nullptr);
                     if (l == 0) stamp(t, 55);
-                    consumer_bar();
-                    if (l == 0) stamp(t, 56);
-                    if (l == 0) dbg_dump(t, 8, ybuf, 512, 512, false);
-                    {
+                    {   // reduce-scatter, warp by warp: warp w's 32 columns all belong to rank w / 2 -- no block barrier, and the
+                        // pushes of the early warps overlap the weight stream of the late ones
+                        __syncwarp();
                         const uint32_t bar = gather_bar(c);
-                        for (int i = c.tid; i < CL_SIZE * c.G * 16; i += CL_CONSUMERS) {   // reduce-scatter: 64 columns to each peer
-                            const int peer = i / (c.G * 16), j = i % (c.G * 16), m = j >> 4, pc = j & 15;
-                            if (l == 0 && i == 0 && stamper) p.ts[(size_t)t * CL_TS_COLS + 72] = timer_after_lds(cl_smem + SM_MISC + 192) + (unsigned long long)(peer + m + pc) * 0ull;
+                        const int peer = c.warp >> 1;
+                        for (int i = c.lane; i < c.G * 8; i += 32) {
+                            const int m = i >> 3, pc = (c.warp & 1) * 8 + (i & 7);
                             const float4 v = *reinterpret_cast<const float4*>(ybuf + m * 512 + peer * CL_NS + pc * 4);
-                            if (l == 0 && i == 0 && stamper) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(v.x) : "memory"); p.ts[(size_t)t * CL_TS_COLS + 70] = now; }
                             st_async_v4(map_to_rank(smem_u32(recv + (c.rank * CL_G + m) * CL_NS + pc * 4), (uint32_t)peer),
                                         __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w),
                                         map_to_rank(bar, (uint32_t)peer));
-                            if (l == 0 && i == 0) stamp(t, 71);
                         }
                     }
                     if (l == 0) stamp(t, 57);

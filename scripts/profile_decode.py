@@ -45,6 +45,11 @@ if (a[:, 52] > 0).any():
         d = lambda i, j: float((w[:, i] - w[:, j]).mean() / 1e3)
         print(f"[{name}] layer 0, us:")
         print("  self-attn: loop %.2f | partial bar %.2f | merge+push %.2f | gather %.2f" % (d(61, 3), d(62, 61), d(63, 62), d(4, 63)))
+        if (w[:, 83] > 0).any():
+            print("  warp-0 attention loop (durations): self wait %.2f | compute %.2f | release+refill %.2f    cross wait %.2f | compute %.2f | release+refill %.2f" % tuple(
+                float(w[:, i].mean() / 1965.0) for i in (82, 83, 84, 85, 86, 87)))   # SM clock cycles at 1965 MHz
+            print("  warp-12 (pair 4) loop (durations)  : self wait %.2f | compute %.2f | release+refill %.2f    cross wait %.2f | compute %.2f | release+refill %.2f" % tuple(
+                float(w[:, i].mean() / 1965.0) for i in (88, 89, 90, 91, 92, 93)))
         print("  O-proj   : gemm+epi %.2f | push %.2f | gather %.2f | LN %.2f" % (d(52, 4), d(53, 52), d(54, 53), d(5, 54)))
         print("  cross    : q2 gemm+bar %.2f | loop %.2f | partial bar %.2f | merge+push %.2f | gather %.2f" % (d(6, 5), d(64, 6), d(65, 64), d(66, 65), d(7, 66)))
         print("  warp-0 GEMM (wait for stage | MMA loop): O-proj %.2f | %.2f   FFN1 %.2f | %.2f   FFN2 %.2f | %.2f" % (d(74, 73), d(75, 74), d(77, 76), d(78, 77), d(80, 79), d(81, 80)))

@@ -94,14 +94,15 @@ TTS_D uint64_t l2_policy_evict_last() {
     return p;
 }
 // ---------------------------------------------------------------- warp-level bf16 MMA (m16n8k16)
-// Decode K/V cache block (decode_cluster.cuh): 64 rows of one (layer, utterance, head) = 8192 bf16.  K rows row-major [64][64];
-// V in four 16-row sub-blocks of 1024 elements stored in mma.m16n8k16 A-FRAGMENT order of V^T [64 d][16 rows]: for the tile
+// Decode K/V cache block (decode_cluster.cuh): 64 rows of one (layer, utterance, head) = 8192 bf16 = four 16-row sub-chunks of
+// 2048 elements [K 16 rows row-major [16][64] | V 16 rows in mma.m16n8k16 A-FRAGMENT order of V^T [64 d][16 rows]]: for the tile
 // dt = d / 16 lane (g = d % 8, t4 = (r % 16) / 4) holds {V[4 t4 + 0..1][g], V[4 t4 + 0..1][g + 8], V[4 t4 + 2..3][g], V[4 t4 + 2..3][g + 8]}
-// as one 16-byte chunk, so the attention loop fetches a whole A fragment with one LDS.128.
-__host__ __device__ __forceinline__ int kv_k_elem(int r, int d) { return r * 64 + d; }
+// as one 16-byte chunk, so the attention loop fetches a whole A fragment with one LDS.128.  Any run of rows [0, 16 n) of a
+// (layer, utterance, head) is one contiguous range of 16 n * 256 bytes: a ring stage is always ONE bulk copy.
+__host__ __device__ __forceinline__ int kv_k_elem(int r, int d) { return (r >> 4) * 2048 + (r & 15) * 64 + d; }
 __host__ __device__ __forceinline__ int kv_v_elem(int r, int d) {
     const int rr = r & 15;
-    return 4096 + (r >> 4) * 1024 + (((d >> 4) * 32 + (d & 7) * 4 + (rr >> 2)) << 3) + ((((rr >> 1) & 1) * 2 + ((d >> 3) & 1)) << 1) + (rr & 1);
+    return (r >> 4) * 2048 + 1024 + (((d >> 4) * 32 + (d & 7) * 4 + (rr >> 2)) << 3) + ((((rr >> 1) & 1) * 2 + ((d >> 3) & 1)) << 1) + (rr & 1);
 }
 
 TTS_D void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {

@@ -47,7 +47,7 @@ constexpr int CL_STAGES = 5, CL_STAGE_BYTES = 32768;
 constexpr int CL_FULL_BARS = 2 * CL_STAGES;
 constexpr int CL_TS_COLS = 128;                      // %globaltimer stamps per decoder step (profiling aid): 0..51 phases, 52.. fine-grained
 constexpr int CL_NS = 512 / CL_SIZE;                 // 64: columns of a 512-wide output owned by one rank
-constexpr int KV_BLOCK_ROWS = 64, KV_BLOCK_ELEMS = 8192;     // one cache block: 64 rows of K + 64 rows of V = 16 KB
+constexpr int KV_BLOCK_ROWS = 64, KV_BLOCK_ELEMS = 8192;     // one cache block: 64 rows = four 16-row sub-chunks [K | V] of 4 KB (common.cuh)
 constexpr int KV_STAGE_ROWS = 128;                   // rows of one pair per ring stage (two blocks)
 constexpr int ATT_WPP = 3;                           // warps per (utterance, head) pair: sub-chunk c of 16 rows -> warp c % 3
 
@@ -177,8 +177,8 @@ TTS_D WSeg wseg(int seg, int rank) {
 }
 
 // Producer: ONE lane issues the whole stage stream of steps [t0, t_end) in order, each stage as soon as its ring slot has
-// been released (the other 31 lanes of the warp park at the group-end barrier).  A weight stage is one bulk copy; a K/V
-// stage is one copy (128 full rows) or up to three (the last, partial stage of a pair, at 16-row granularity).  It arrives
+// been released (the other 31 lanes of the warp park at the group-end barrier).  Every stage is ONE bulk copy: 32 KB of
+// weights, or up to 128 rows of one pair's K/V (16-row granularity; the cache layout keeps them contiguous).  It arrives
 // on the slot's empty barrier on behalf of the warps that do not read the stage.  Stops early when the consumers raise flags[1].
 TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* full, uint64_t* empty, volatile int* flags,
                        const volatile int* glens, int rank, int b0, int G, int t0, int t_end) {
@@ -216,18 +216,9 @@ TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* fu
                         const int r16 = (rows + 15) & ~15;
                         const bf16* src = cache + kv_block_offset(l, p.B, b0 + pair, rank, nblk, 2 * j);
                         if (r16 == 0) mbar_arrive(fbar);
-                        else {
+                        else {                           // rows [128 j, 128 j + r16) of the pair are one contiguous range
                             mbar_expect_tx(fbar, (uint32_t)r16 * 256u);
-                            if (r16 == KV_STAGE_ROWS) bulk_g2s(dst, src, 32768u, fbar, pol_kv);
-                            else {
-                                int rem = r16, off = 0;
-                                if (rem >= KV_BLOCK_ROWS) { bulk_g2s(dst, src, 16384u, fbar, pol_kv); rem -= KV_BLOCK_ROWS; off = 16384; }
-                                if (rem > 0) {
-                                    const unsigned char* s2 = reinterpret_cast<const unsigned char*>(src) + off;
-                                    bulk_g2s(dst + off, s2, (uint32_t)rem * 128u, fbar, pol_kv);
-                                    bulk_g2s(dst + off + 8192, s2 + 8192, (uint32_t)rem * 128u, fbar, pol_kv);
-                                }
-                            }
+                            bulk_g2s(dst, src, (uint32_t)r16 * 256u, fbar, pol_kv);
                         }
                         mbar_arrive_n(&empty[stage], (uint32_t)(CL_WARPS - ATT_WPP));
                         ++issued;
@@ -481,7 +472,7 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, cons
                 for (int s2 = 0; s2 < 3; ++s2) {
                     if (s2 < nsc) {
                         const int c8 = c0 + 3 * s2;
-                        const unsigned char* kb = st + (c8 >> 2) * 16384 + (c8 & 3) * 2048 + krow_off;
+                        const unsigned char* kb = st + c8 * 4096 + krow_off;
                         float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
                         uint4 kr[2][2];
 #pragma unroll
@@ -531,7 +522,7 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, cons
                 for (int s2 = 0; s2 < 3; ++s2) {
                     if (s2 < nsc) {
                         const int c8 = c0 + 3 * s2;
-                        const unsigned char* vb = st + (c8 >> 2) * 16384 + 8192 + (c8 & 3) * 2048 + c.lane * 16;
+                        const unsigned char* vb = st + c8 * 4096 + 2048 + c.lane * 16;
                         const float p0 = fast_exp2(v[s2][0][0] - mnew), p1 = fast_exp2(v[s2][0][1] - mnew);
                         const float p2 = fast_exp2(v[s2][1][0] - mnew), p3 = fast_exp2(v[s2][1][1] - mnew);
                         l += (p0 + p1) + (p2 + p3);      // this lane's rows only (the other 7 lanes of the column group hold copies)

@@ -80,14 +80,14 @@ TTS_D void gemm_store(const GemmParams& p, int m, int n, float v0, float v1) {
     }
     if (p.scatter == SC_CROSS_KV_VT) {
         // decode kernel (decode_cluster.cuh): per (layer, b, h) 64-row blocks of 8192 elements,
-        // [K rows row-major [64][64] | V in four 16-row sub-blocks in MMA A-fragment order (kv_v_elem)]; Lpad = 64 * blocks
+        // four 16-row sub-chunks [K rows | V in MMA A-fragment order] (kv_k_elem / kv_v_elem, common.cuh); Lpad = 64 * blocks
         const int layer = n >> 10, kv = (n >> 9) & 1, h = (n >> 6) & 7, d = n & 63, r = t & 63;
         bf16* blk = p.out_bf16 + ((((size_t)layer * p.B + b) * kHeads + h) * (size_t)(p.Lpad >> 6) + (t >> 6)) * 8192;
         if (kv) {
             blk[kv_v_elem(r, d)] = __float2bfloat16(v0);
             blk[kv_v_elem(r, d + 1)] = __float2bfloat16(v1);
         } else {
-            *reinterpret_cast<uint32_t*>(blk + r * kDHead + d) = pack_bf16x2(v0, v1);
+            *reinterpret_cast<uint32_t*>(blk + kv_k_elem(r, d)) = pack_bf16x2(v0, v1);
         }
         return;
     }

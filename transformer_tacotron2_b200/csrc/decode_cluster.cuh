@@ -349,27 +349,27 @@ TTS_D void gather_sync(ClCtx& c) {
     ++c.gphase;
 }
 // One warp pushes rows [0, G) x 16 fp32 columns of its private staging tile (row stride 16 floats) to dst[m][0..16)
-// (row stride dld) of every peer.
+// (row stride dld) of every peer.  Lanes 4 p .. 4 p + 3 serve peer p (one 16-byte column chunk each, all rows): the remote
+// addresses are mapped once per lane and the loop has no index arithmetic.
 TTS_D void push_tile_f32(const ClCtx& c, const float* wst, float* dst, int dld) {
-    const uint32_t bar = gather_bar(c);
-    const int per_peer = c.G * 4;
-    for (int i = c.lane; i < per_peer * CL_SIZE; i += 32) {
-        const int peer = i / per_peer, j = i - peer * per_peer, m = j >> 2, pc = j & 3;
+    const uint32_t peer = (uint32_t)c.lane >> 2; const int pc = c.lane & 3;
+    const uint32_t bar = map_to_rank(gather_bar(c), peer);
+    const uint32_t rdst = map_to_rank(smem_u32(dst + pc * 4), peer);
+    for (int m = 0; m < c.G; ++m) {
         const float4 v = *reinterpret_cast<const float4*>(wst + m * 16 + pc * 4);
-        st_async_v4(map_to_rank(smem_u32(dst + m * dld + pc * 4), (uint32_t)peer),
-                    __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w), map_to_rank(bar, (uint32_t)peer));
+        st_async_v4(rdst + (uint32_t)(m * dld * 4), __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w), bar);
     }
 }
-// same, as bf16 (16 columns = two 16-byte chunks per row)
+// same, as bf16 (16 columns = two 16-byte chunks per row; the 2 G chunks of a peer go round its four lanes)
 TTS_D void push_tile_bf16(const ClCtx& c, const float* wst, bf16* dst, int dld) {
-    const uint32_t bar = gather_bar(c);
-    const int per_peer = c.G * 2;
-    for (int i = c.lane; i < per_peer * CL_SIZE; i += 32) {
-        const int peer = i / per_peer, j = i - peer * per_peer, m = j >> 1, pc = j & 1;
+    const uint32_t peer = (uint32_t)c.lane >> 2;
+    const uint32_t bar = map_to_rank(gather_bar(c), peer);
+    const uint32_t rdst = map_to_rank(smem_u32(dst), peer);
+    for (int j = c.lane & 3; j < c.G * 2; j += 4) {
+        const int m = j >> 1, pc = j & 1;
         const float4 v0 = *reinterpret_cast<const float4*>(wst + m * 16 + pc * 8);
         const float4 v1 = *reinterpret_cast<const float4*>(wst + m * 16 + pc * 8 + 4);
-        st_async_v4(map_to_rank(smem_u32(dst + m * dld + pc * 8), (uint32_t)peer),
-                    pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w), map_to_rank(bar, (uint32_t)peer));
+        st_async_v4(rdst + (uint32_t)((m * dld + pc * 8) * 2), pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w), bar);
     }
 }
 
@@ -819,24 +819,33 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         }
                     }
                     if (l == 0) stamp(t, 57);
+                    // my 64 columns: 8 partials (fixed order) + bias + residual -> every peer's ybuf.  Four threads per (row, 4-column
+                    // chunk), two peers each; bias and residual are fetched before the wait
+                    const bool reducer = c.tid < c.G * 64;
+                    const int rm = c.tid >> 6, rpc = (c.tid >> 2) & 15, rcol = c.rank * CL_NS + rpc * 4, rq = c.tid & 3;
+                    float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (reducer) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(W.b2 + rcol));
+                        const float4 xr = *reinterpret_cast<const float4*>(xres + rm * 512 + rcol);
+                        racc = make_float4(bb.x + xr.x, bb.y + xr.y, bb.z + xr.z, bb.w + xr.w);
+                    }
                     gather_sync(c);
                     if (l == 0) stamp(t, 58);
                     if (l == 0) dbg_dump(t, 10, recv, 2560, 2560, false);
-                    if (c.tid < c.G * 16) {              // my 64 columns: 8 partials (fixed order) + bias + residual -> every peer's ybuf
-                        const int m = c.tid >> 4, pc = c.tid & 15, col = c.rank * CL_NS + pc * 4;
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(W.b2 + col));
-                        const float4 xr = *reinterpret_cast<const float4*>(xres + m * 512 + col);
-                        float4 v = make_float4(bb.x + xr.x, bb.y + xr.y, bb.z + xr.z, bb.w + xr.w);
+                    if (reducer) {
+                        float4 v = racc;
 #pragma unroll
                         for (int r = 0; r < CL_SIZE; ++r) {
-                            const float4 q = *reinterpret_cast<const float4*>(recv + (r * CL_G + m) * CL_NS + pc * 4);
+                            const float4 q = *reinterpret_cast<const float4*>(recv + (r * CL_G + rm) * CL_NS + rpc * 4);
                             v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
                         }
-                        const uint32_t bar = gather_bar(c);
+                        const uint32_t bar = gather_bar(c), dsta = smem_u32(ybuf + rm * 512 + rcol);
 #pragma unroll
-                        for (int peer = 0; peer < CL_SIZE; ++peer)
-                            st_async_v4(map_to_rank(smem_u32(ybuf + m * 512 + col), (uint32_t)peer), __float_as_uint(v.x), __float_as_uint(v.y),
-                                        __float_as_uint(v.z), __float_as_uint(v.w), map_to_rank(bar, (uint32_t)peer));
+                        for (int k = 0; k < 2; ++k) {
+                            const uint32_t peer = (uint32_t)(2 * rq + k);
+                            st_async_v4(map_to_rank(dsta, peer), __float_as_uint(v.x), __float_as_uint(v.y),
+                                        __float_as_uint(v.z), __float_as_uint(v.w), map_to_rank(bar, peer));
+                        }
                     }
                     if (l == 0) stamp(t, 59);
                     cp_async_wait<0>();

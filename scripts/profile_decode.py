@@ -53,6 +53,8 @@ if (a[:, 52] > 0).any():
         print("  O-proj   : gemm+epi %.2f | push %.2f | gather %.2f | LN %.2f" % (d(52, 4), d(53, 52), d(54, 53), d(5, 54)))
         print("  cross    : q2 gemm+bar %.2f | loop %.2f | partial bar %.2f | merge+push %.2f | gather %.2f" % (d(6, 5), d(64, 6), d(65, 64), d(66, 65), d(7, 66)))
         print("  warp-0 GEMM (wait for stage | MMA loop): O-proj %.2f | %.2f   FFN1 %.2f | %.2f   FFN2 %.2f | %.2f" % (d(74, 73), d(75, 74), d(77, 76), d(78, 77), d(80, 79), d(81, 80)))
+        if (w[:, 94] > 0).any():
+            print("  y3 detail: rs gather done -> reduced %.2f | -> pushed %.2f" % (d(94, 58), d(59, 94)))
         print("  FFN      : ffn1 %.2f | ffn2 gemm (warp 0) %.2f | rs push (warp 0) %.2f | rs gather %.2f | reduce+y3 push %.2f | y3 gather %.2f | LN %.2f" % (
             d(9, 8), d(55, 9), d(57, 55), d(58, 57), d(59, 58), d(60, 59), d(10, 60)))
 print("mean us/step", out["us_per_step_mean"], " roofline us/step", decode_bytes(B, T, S) / T / 6468.6e3)

@@ -283,17 +283,21 @@ TTS_D void cl_gemm(ClCtx& c, int na, const bf16* X, int ldx, BiasFn biasf, Epi e
         const uint4* wp = reinterpret_cast<const uint4*>(cl_acquire(c, idx) + (c.warp % WPS) * BW);
         if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "l"(wp) : "memory"); tstamp[1] = now; }
         const bf16* xrow = X + (c.lane & 7) * ldx + (c.lane >> 3) * 8;
+#pragma unroll 1
+        for (int kq = 0; kq < KP / 4; ++kq) {            // four k-steps per iteration: a fully unrolled K loop in every GEMM makes
+#pragma unroll                                           // the kernel too large for the instruction cache
+            for (int ku = 0; ku < 4; ++ku) {
+                const int kp = kq * 4 + ku;
+                uint32_t bfrag[4];
+                ldmatrix_x4(bfrag, xrow + kp * 32);
 #pragma unroll
-        for (int kp = 0; kp < KP; ++kp) {
-            uint32_t bfrag[4];
-            ldmatrix_x4(bfrag, xrow + kp * 32);
-#pragma unroll
-            for (int j = 0; j < TW; ++j) {
-                const uint4 w0 = wp[((kp * TW + j) * 2) * 32 + c.lane];
-                const uint4 w1 = wp[((kp * TW + j) * 2 + 1) * 32 + c.lane];
-                const uint32_t a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w};
-                mma_bf16_16816(acc[j][kp % NCH], a0, bfrag[0], bfrag[1]);
-                mma_bf16_16816(acc[j][kp % NCH], a1, bfrag[2], bfrag[3]);
+                for (int j = 0; j < TW; ++j) {
+                    const uint4 w0 = wp[((kp * TW + j) * 2) * 32 + c.lane];
+                    const uint4 w1 = wp[((kp * TW + j) * 2 + 1) * 32 + c.lane];
+                    const uint32_t a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w};
+                    mma_bf16_16816(acc[j][ku % NCH], a0, bfrag[0], bfrag[1]);
+                    mma_bf16_16816(acc[j][ku % NCH], a1, bfrag[2], bfrag[3]);
+                }
             }
         }
         if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(acc[0][0][0]), "f"(acc[TW - 1][NCH - 1][3]) : "memory"); tstamp[2] = now; }
@@ -596,6 +600,9 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, cons
 }
 
 // ---------------------------------------------------------------- the kernel
+// DBG = false is the product kernel: the %globaltimer stamps and the debug dumps are compiled out (the kernel is bound by
+// instruction fetch at every phase boundary -- profiles/r02_decode_summary.md -- so code that never runs still costs time).
+template <bool DBG>
 __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __grid_constant__ ClusterParams p, int t0, int n_steps) {
     extern __shared__ __align__(128) unsigned char cl_smem[];
     ClCtx c;
@@ -626,7 +633,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
     bf16* h2 = reinterpret_cast<bf16*>(cl_smem + SM_H2);
     bf16* fbuf = reinterpret_cast<bf16*>(cl_smem + SM_FBUF);
     float* wst = reinterpret_cast<float*>(cl_smem + SM_WST) + (c.warp & 3) * (CL_G * 16);    // private epilogue tile [G][16] of warps 0..3 (the narrow GEMMs)
-    const bool stamper = p.ts != nullptr && cid == 0 && c.rank == 0 && c.tid == 0;
+    const bool stamper = DBG && p.ts != nullptr && cid == 0 && c.rank == 0 && c.tid == 0;
     auto stamp = [&](int t, int idx) {
         if (stamper) {
             // BAR.SYNC does not block at issue (the warp stalls at the next instruction that touches barrier-protected state): a
@@ -639,7 +646,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
     };
 
     // debug dump: slot `slot` <- rows [0, G) x n values (row stride ld) of a shared-memory buffer, widened to fp32
-    const bool dumper = p.dbg != nullptr && cid == 0 && c.rank == p.dbg_rank && !is_producer;
+    const bool dumper = DBG && p.dbg != nullptr && cid == 0 && c.rank == p.dbg_rank && !is_producer;
     auto dbg_dump = [&](int t, int slot, const void* src, int ld, int n, bool is_bf16) {
         if (dumper && t == t0) {
             for (int i = c.tid; i < c.G * n; i += CL_CONSUMERS) {

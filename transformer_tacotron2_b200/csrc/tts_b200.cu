@@ -543,14 +543,15 @@ extern "C" int tts_decode_begin(TtsHandle* h, void* ws, int B, int S, int max_le
 
     if (h->cluster_ok < 0) {                                            // how many 8-CTA clusters of this kernel can be co-resident?
         h->cluster_ok = 0;
-        if (cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES) == cudaSuccess) {
+        if (cudaFuncSetAttribute(decode_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES) == cudaSuccess &&
+            cudaFuncSetAttribute(decode_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM_BYTES) == cudaSuccess) {
             cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
             cfg.gridDim = dim3(CL_SIZE * 8); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = CL_SMEM_BYTES;
             cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = CL_SIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel, &cfg) == cudaSuccess && n > 0) { h->cluster_ok = 1; h->max_clusters = n; }
+            if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel<true>, &cfg) == cudaSuccess && n > 0) { h->cluster_ok = 1; h->max_clusters = n; }
         }
         cudaGetLastError();
     }
@@ -598,7 +599,8 @@ extern "C" int tts_decode_steps(TtsHandle* h, void* ws, int n_steps, void* strea
     }
     h->cparams.dbg_rank = h->decode_debug - 1;
     h->cparams.dbg = h->decode_debug ? wsp<float>(ws, Ws::make(h->dec_B, h->dec_S, h->dec_T).wide) : nullptr;
-    CK(cudaLaunchKernelEx(&cfg, decode_cluster_kernel, h->cparams, h->dec_t, n_steps));
+    if (h->cparams.ts || h->cparams.dbg) CK(cudaLaunchKernelEx(&cfg, decode_cluster_kernel<true>, h->cparams, h->dec_t, n_steps));
+    else CK(cudaLaunchKernelEx(&cfg, decode_cluster_kernel<false>, h->cparams, h->dec_t, n_steps));
     ++launch_counter();
     h->dec_t += n_steps;                                                // upper bound; tts_decode_status refines it
     return 0;

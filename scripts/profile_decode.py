@@ -50,11 +50,13 @@ if (a[:, 52] > 0).any():
                 float(w[:, i].mean() / 1965.0) for i in (82, 83, 84, 85, 86, 87)))   # SM clock cycles at 1965 MHz
             print("  warp-12 (pair 4) loop (durations)  : self wait %.2f | compute %.2f | release+refill %.2f    cross wait %.2f | compute %.2f | release+refill %.2f" % tuple(
                 float(w[:, i].mean() / 1965.0) for i in (88, 89, 90, 91, 92, 93)))
-        print("  O-proj   : gemm+epi %.2f | LayerNorm by owner (stats exchange, normalise, row exchange) %.2f" % (d(52, 4), d(5, 52)))
+        print("  O-proj   : gemm+epi %.2f | push %.2f | gather %.2f | LN %.2f" % (d(52, 4), d(53, 52), d(54, 53), d(5, 54)))
         print("  cross    : q2 gemm+bar %.2f | loop %.2f | partial bar %.2f | merge+push %.2f | gather %.2f" % (d(6, 5), d(64, 6), d(65, 64), d(66, 65), d(7, 66)))
         print("  warp-0 GEMM (wait for stage | MMA loop): O-proj %.2f | %.2f   FFN1 %.2f | %.2f   FFN2 %.2f | %.2f" % (d(74, 73), d(75, 74), d(77, 76), d(78, 77), d(80, 79), d(81, 80)))
-        print("  FFN      : ffn1 %.2f | ffn2 gemm (warp 0) %.2f | rs push (warp 0) %.2f | rs gather %.2f | reduce %.2f | LayerNorm by owner %.2f" % (
-            d(9, 8), d(55, 9), d(57, 55), d(58, 57), d(59, 58), d(10, 59)))
+        if (w[:, 94] > 0).any():
+            print("  y3 detail: rs gather done -> reduced %.2f | -> pushed %.2f" % (d(94, 58), d(59, 94)))
+        print("  FFN      : ffn1 %.2f | ffn2 gemm (warp 0) %.2f | rs push (warp 0) %.2f | rs gather %.2f | reduce+y3 push %.2f | y3 gather %.2f | LN %.2f" % (
+            d(9, 8), d(55, 9), d(57, 55), d(58, 57), d(59, 58), d(60, 59), d(10, 60)))
 print("mean us/step", out["us_per_step_mean"], " roofline us/step", decode_bytes(B, T, S) / T / 6468.6e3)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/phase_times.json", "w"), indent=1)

@@ -332,22 +332,13 @@ TTS_D void st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c2, uint3
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
                  ::"r"(addr), "r"(a), "r"(b), "r"(c2), "r"(d), "r"(remote_bar) : "memory");
 }
-TTS_D void st_async_v2(uint32_t addr, uint32_t a, uint32_t b, uint32_t remote_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1,%2}, [%3];"
-                 ::"r"(addr), "r"(a), "r"(b), "r"(remote_bar) : "memory");
-}
-// Gather phases of one decoder step: 3 (prenet) + 9 per layer {attention, LN1 stats, LN1 rows, cross-attention, LN2 stats,
-// LN2 rows, FFN2 reduce-scatter, LN3 stats, LN3 rows} + 1 (heads)
-constexpr int CL_PHASES = 3 + 9 * 6 + 1;
-// expected bytes of gather phase ph (0 .. CL_PHASES - 1 within a step) at every receiver
+// expected bytes of gather phase ph (0..39 within a step) at every receiver
 TTS_D uint32_t gather_bytes(int ph, int G) {
     if (ph < 2) return 512u * G;                         // prenet fc1 / fc2: 8 ranks x G x 32 cols bf16
-    if (ph == 2) return 1024u * G;                       // prenet proj: 8 x G x 64 bf16 (the fp32 residual stays with its owner)
-    if (ph == CL_PHASES - 1) return 160u * G + 128u;     // head: 5 ranks x G x 16 cols bf16 + one 16-byte record per rank
-    const int k = (ph - 3) % 9;
-    if (k == 6) return 2048u * G;                        // FFN2 reduce-scatter: 8 ranks x G x 64 f32
-    if (k == 1 || k == 4 || k == 7) return 256u * G;     // LayerNorm statistics: 8 ranks x 4 warps x G x (sum, sum of squares)
-    return 1024u * G;                                    // attention outputs / normalised rows: 8 x G x 64 bf16
+    if (ph == 2) return 3072u * G;                       // prenet proj: 8 x G x 64 x (f32 + bf16)
+    if (ph == 39) return 160u * G + 128u;                // head: 5 ranks x G x 16 cols bf16 + one 16-byte record per rank
+    const int k = (ph - 3) % 6;
+    return (k == 0 || k == 2) ? 1024u * G : 2048u * G;   // attention outputs (bf16) : f32 slices (O, O2, reduce-scatter, y3)
 }
 TTS_D uint32_t gather_bar(const ClCtx& c) { return smem_u32(&c.gsync[c.gphase & 1]); }
 // Block-wide completion of the current gather phase: warp 0 waits on the mbarrier (one warp polling instead of sixteen),
@@ -356,14 +347,24 @@ TTS_D void gather_sync(ClCtx& c) {
     if (c.warp == 0) {
         uint64_t* bar = &c.gsync[c.gphase & 1];
         mbar_wait(bar, (c.gphase >> 1) & 1);
-        if (c.lane == 0) mbar_expect_tx(bar, gather_bytes((int)((c.gphase + 2) % CL_PHASES), c.G));
+        if (c.lane == 0) mbar_expect_tx(bar, gather_bytes((int)((c.gphase + 2) % 40), c.G));
     }
     consumer_bar();
     ++c.gphase;
 }
-// One warp pushes rows [0, G) x 16 columns of its private fp32 staging tile (row stride 16 floats) as bf16 to dst[m][0..16)
-// (row stride dld) of every peer: two 16-byte chunks per row.  Lanes 4 p .. 4 p + 3 serve peer p (the 2 G chunks go round
-// them): the remote addresses are mapped once per lane and the loop has no index arithmetic.
+// One warp pushes rows [0, G) x 16 fp32 columns of its private staging tile (row stride 16 floats) to dst[m][0..16)
+// (row stride dld) of every peer.  Lanes 4 p .. 4 p + 3 serve peer p (one 16-byte column chunk each, all rows): the remote
+// addresses are mapped once per lane and the loop has no index arithmetic.
+TTS_D void push_tile_f32(const ClCtx& c, const float* wst, float* dst, int dld) {
+    const uint32_t peer = (uint32_t)c.lane >> 2; const int pc = c.lane & 3;
+    const uint32_t bar = map_to_rank(gather_bar(c), peer);
+    const uint32_t rdst = map_to_rank(smem_u32(dst + pc * 4), peer);
+    for (int m = 0; m < c.G; ++m) {
+        const float4 v = *reinterpret_cast<const float4*>(wst + m * 16 + pc * 4);
+        st_async_v4(rdst + (uint32_t)(m * dld * 4), __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w), bar);
+    }
+}
+// same, as bf16 (16 columns = two 16-byte chunks per row; the 2 G chunks of a peer go round its four lanes)
 TTS_D void push_tile_bf16(const ClCtx& c, const float* wst, bf16* dst, int dld) {
     const uint32_t peer = (uint32_t)c.lane >> 2;
     const uint32_t bar = map_to_rank(gather_bar(c), peer);
@@ -376,68 +377,48 @@ TTS_D void push_tile_bf16(const ClCtx& c, const float* wst, bf16* dst, int dld) 
     }
 }
 
-// LayerNorm by the OWNER of the columns.  Warps 0..3 hold the pre-LN values of this rank's 64 columns in their private tiles
-// wst[G][16]; the row statistics need all 512 columns, the normalisation does not: every warp pushes its per-row (sum, sum of
-// squares) to all peers (8 bytes per row), each rank combines the 32 partials of a row, normalises ITS columns, keeps the fp32
-// result as its slice of the residual stream (xres: only the owner ever reads it) and pushes the bf16 rows into every peer's
-// xa -- the next GEMM's operand.  Two small exchanges instead of an fp32 all-gather followed by a redundant full-row LayerNorm.
-// The affine parameters of the rank's columns are fetched into shared memory by ln_prefetch() before the GEMM.
+// LayerNorm of the gathered rows: ybuf -> xres (f32) + xa (bf16); warp m < G owns row m.  The affine parameters
+// (global memory) are fetched asynchronously into shared memory by ln_prefetch() BEFORE the exchange the rows are
+// waited on; the caller's gather_sync() orders both (cp.async.wait_group precedes its barrier).
 TTS_D void ln_prefetch(const ClCtx& c, const float* g, const float* b) {
-    float* dst = reinterpret_cast<float*>(c.smem + SM_RED + 4096);        // [0,64) gamma, [64,128) beta of columns rank*64 ..
-    if (c.tid < 32) cp_async_16(dst + c.tid * 4, (c.tid < 16 ? g : b) + c.rank * CL_NS + (c.tid & 15) * 4, true);
+    float* dst = reinterpret_cast<float*>(c.smem + SM_RED + 4096);        // [0,512) gamma, [512,1024) beta
+    if (c.tid < 256) {
+        const float* src = (c.tid < 128 ? g : b) + (c.tid & 127) * 4;
+        cp_async_16(dst + c.tid * 4, src, true);
+    }
     cp_async_commit();
 }
-// All 16 consumer warps call this (it contains the two exchanges); `wst` is the caller's tile (warps 0..3).
-TTS_D void cl_ln_owner(ClCtx& c, float* wst, float ln_eps) {
-    float* stat = reinterpret_cast<float*>(c.smem + SM_RED + 2048);       // [32 partials = rank * 4 + warp][8 rows][sum, sumsq]
-    const int m = c.lane >> 2, q = c.lane & 3;                            // lane <-> (row, 4-column chunk) of the tile
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c.warp < 4) {
-        __syncwarp();
-        float s = 0.f, ss = 0.f;
-        if (m < c.G) {
-            v = *reinterpret_cast<const float4*>(wst + m * 16 + q * 4);
-            s = (v.x + v.y) + (v.z + v.w);
-            ss = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-        if (m < c.G) {                                   // the four lanes of a row send to two peers each
-            const uint32_t bar = gather_bar(c), dsta = smem_u32(stat + ((c.rank * 4 + c.warp) * 8 + m) * 2);
+TTS_D void cl_layernorm(ClCtx& c, float ln_eps) {
+    if (c.warp < c.G) {
+        const float* y = reinterpret_cast<const float*>(c.smem + SM_YBUF) + c.warp * 512;
+        const float* gb = reinterpret_cast<const float*>(c.smem + SM_RED + 4096);
+        float* xr = reinterpret_cast<float*>(c.smem + SM_XRES) + c.warp * 512;
+        bf16* xa = reinterpret_cast<bf16*>(c.smem + SM_XA) + c.warp * LDX512;
+        float v[16];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const uint32_t peer = (uint32_t)(2 * q + k);
-                st_async_v2(map_to_rank(dsta, peer), __float_as_uint(s), __float_as_uint(ss), map_to_rank(bar, peer));
-            }
+        for (int i = 0; i < 4; ++i) {
+            const float4 x = *reinterpret_cast<const float4*>(y + i * 128 + c.lane * 4);
+            v[i * 4] = x.x; v[i * 4 + 1] = x.y; v[i * 4 + 2] = x.z; v[i * 4 + 3] = x.w;
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += v[i];
+        const float mean = warp_sum(s) * (1.f / 512.f);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; ss += d * d; }
+        const float rstd = rsqrtf(warp_sum(ss) * (1.f / 512.f) + ln_eps);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int col = i * 128 + c.lane * 4;
+            const float4 g4 = *reinterpret_cast<const float4*>(gb + col), b4 = *reinterpret_cast<const float4*>(gb + 512 + col);
+            const float o0 = (v[i * 4] - mean) * rstd * g4.x + b4.x, o1 = (v[i * 4 + 1] - mean) * rstd * g4.y + b4.y;
+            const float o2 = (v[i * 4 + 2] - mean) * rstd * g4.z + b4.z, o3 = (v[i * 4 + 3] - mean) * rstd * g4.w + b4.w;
+            *reinterpret_cast<float4*>(xr + col) = make_float4(o0, o1, o2, o3);
+            *reinterpret_cast<uint2*>(xa + col) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
         }
     }
-    cp_async_wait<0>();
-    gather_sync(c);
-    if (c.warp < 4) {
-        float s = 0.f, ss = 0.f;
-        if (m < c.G) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {                // fixed order: partials 8 q .. 8 q + 7, then the four lanes
-                const float2 pr = *reinterpret_cast<const float2*>(stat + ((q * 8 + k) * 8 + m) * 2);
-                s += pr.x; ss += pr.y;
-            }
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-        if (m < c.G) {
-            const float mean = s * (1.f / 512.f);
-            const float rstd = rsqrtf(fmaxf(ss * (1.f / 512.f) - mean * mean, 0.f) + ln_eps);
-            const float* gb = reinterpret_cast<const float*>(c.smem + SM_RED + 4096) + c.warp * 16 + q * 4;
-            const float4 g4 = *reinterpret_cast<const float4*>(gb), b4 = *reinterpret_cast<const float4*>(gb + 64);
-            const float4 y = make_float4((v.x - mean) * rstd * g4.x + b4.x, (v.y - mean) * rstd * g4.y + b4.y,
-                                         (v.z - mean) * rstd * g4.z + b4.z, (v.w - mean) * rstd * g4.w + b4.w);
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(c.smem + SM_XRES) + m * 512 + c.rank * CL_NS + c.warp * 16 + q * 4) = y;
-            *reinterpret_cast<float4*>(wst + m * 16 + q * 4) = y;
-        }
-        __syncwarp();
-        push_tile_bf16(c, wst, reinterpret_cast<bf16*>(c.smem + SM_XA) + c.rank * CL_NS + c.warp * 16, LDX512);
-    }
-    gather_sync(c);
+    consumer_bar();
 }
 
 // Attention of this CTA's pairs (utterance gi of the group, head = rank).  Warps 3 gi .. 3 gi + 2 own pair gi; the cache rows
@@ -752,8 +733,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                             const int col = c.rank * CL_NS + ti * 16 + n;
                             return __ldg(p.b_proj + col) + p.dec_alpha * __ldg(p.pe + (size_t)t * kDModel + col);
                         },
-                        [&](int ti, int n, int m, float v) { wst[m * 16 + n] = v; xres[m * 512 + c.rank * CL_NS + ti * 16 + n] = v; });
-                if (c.warp < 4) { __syncwarp(); push_tile_bf16(c, wst, xa + c.rank * CL_NS + c.warp * 16, LDX512); }
+                        [&](int, int n, int m, float v) { wst[m * 16 + n] = v; });
+                if (c.warp < 4) {
+                    __syncwarp();
+                    push_tile_f32(c, wst, xres + c.rank * CL_NS + c.warp * 16, 512);
+                    push_tile_bf16(c, wst, xa + c.rank * CL_NS + c.warp * 16, LDX512);
+                }
                 gather_sync(c);
                 stamp(t, 2);
                 dbg_dump(t, 0, xa, LDX512, 512, true);
@@ -785,7 +770,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                             [&](int ti, int n, int m, float v) { wst[m * 16 + n] = v + xres[m * 512 + c.rank * CL_NS + ti * 16 + n]; },
                             (stamper && l == 0) ? p.ts + (size_t)t * CL_TS_COLS + 73 : nullptr);
                     if (l == 0) stamp(t, 52);
-                    cl_ln_owner(c, wst, p.ln_eps);
+                    if (c.warp < 4) { __syncwarp(); push_tile_f32(c, wst, ybuf + c.rank * CL_NS + c.warp * 16, 512); }
+                    if (l == 0) stamp(t, 53);
+                    cp_async_wait<0>();
+                    gather_sync(c);
+                    if (l == 0) stamp(t, 54);
+                    cl_layernorm(c, p.ln_eps);
                     stamp(t, 5 + 8 * l);
                     if (l == 0) dbg_dump(t, 3, xa, LDX512, 512, true);
                     // ---- cross-attention query of head `rank` (local)
@@ -802,7 +792,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     cl_gemm<16, 1>(c, 4, abuf, LDX512,
                             [&](int ti, int n) { return __ldg(W.bo2 + c.rank * CL_NS + ti * 16 + n); },
                             [&](int ti, int n, int m, float v) { wst[m * 16 + n] = v + xres[m * 512 + c.rank * CL_NS + ti * 16 + n]; });
-                    cl_ln_owner(c, wst, p.ln_eps);
+                    if (c.warp < 4) { __syncwarp(); push_tile_f32(c, wst, ybuf + c.rank * CL_NS + c.warp * 16, 512); }
+                    cp_async_wait<0>();
+                    gather_sync(c);
+                    cl_layernorm(c, p.ln_eps);
                     stamp(t, 8 + 8 * l);
                     if (l == 0) dbg_dump(t, 5, xa, LDX512, 512, true);
                     // ---- FFN: hidden slice [256 rank, +256) stays local (bf16); FFN2 is split along K
@@ -833,14 +826,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         }
                     }
                     if (l == 0) stamp(t, 57);
-                    // my 64 columns: 8 partials (fixed order) + bias + residual -> this warp's tile (warps 0..3, lane <-> row and
-                    // 4-column chunk, the layout cl_ln_owner expects); bias and residual are fetched before the wait
-                    const int lm = c.lane >> 2, lq = c.lane & 3, rcol = c.rank * CL_NS + (c.warp & 3) * 16 + lq * 4;
-                    const bool reducer = c.warp < 4 && lm < c.G;
+                    // my 64 columns: 8 partials (fixed order) + bias + residual -> every peer's ybuf.  Four threads per (row, 4-column
+                    // chunk), two peers each; bias and residual are fetched before the wait
+                    const bool reducer = c.tid < c.G * 64;
+                    const int rm = c.tid >> 6, rpc = (c.tid >> 2) & 15, rcol = c.rank * CL_NS + rpc * 4, rq = c.tid & 3;
                     float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (reducer) {
                         const float4 bb = __ldg(reinterpret_cast<const float4*>(W.b2 + rcol));
-                        const float4 xr = *reinterpret_cast<const float4*>(xres + lm * 512 + rcol);
+                        const float4 xr = *reinterpret_cast<const float4*>(xres + rm * 512 + rcol);
                         racc = make_float4(bb.x + xr.x, bb.y + xr.y, bb.z + xr.z, bb.w + xr.w);
                     }
                     gather_sync(c);
@@ -850,13 +843,23 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                         float4 v = racc;
 #pragma unroll
                         for (int r = 0; r < CL_SIZE; ++r) {
-                            const float4 q = *reinterpret_cast<const float4*>(recv + (r * CL_G + lm) * CL_NS + (c.warp & 3) * 16 + lq * 4);
+                            const float4 q = *reinterpret_cast<const float4*>(recv + (r * CL_G + rm) * CL_NS + rpc * 4);
                             v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
                         }
-                        *reinterpret_cast<float4*>(wst + lm * 16 + lq * 4) = v;
+                        const uint32_t bar = gather_bar(c), dsta = smem_u32(ybuf + rm * 512 + rcol);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const uint32_t peer = (uint32_t)(2 * rq + k);
+                            st_async_v4(map_to_rank(dsta, peer), __float_as_uint(v.x), __float_as_uint(v.y),
+                                        __float_as_uint(v.z), __float_as_uint(v.w), map_to_rank(bar, peer));
+                        }
                     }
                     if (l == 0) stamp(t, 59);
-                    cl_ln_owner(c, wst, p.ln_eps);
+                    cp_async_wait<0>();
+                    gather_sync(c);
+                    if (l == 0) stamp(t, 60);
+                    if (l == 0) dbg_dump(t, 9, ybuf, 512, 512, false);
+                    cl_layernorm(c, p.ln_eps);
                     stamp(t, 10 + 8 * l);
                     if (l == 0) dbg_dump(t, 7, xa, LDX512, 512, true);
                 }

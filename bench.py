@@ -194,14 +194,24 @@ def run_b200(args, rank, world, local_rank):
     import datetime
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # short collective timeout: a rank that dies must not park its peers in a barrier for the default 10 minutes
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=args.nccl_timeout))
     from transformer_tacotron2_b200 import _lib as _libmod
-    if world > 1:                                                   # one builder per node, then everybody loads the finished library
-        if local_rank == 0:
-            _libmod.load()
-        dist.barrier()
+    if world > 1:
+        # NCCL announces its version on stdout when the first communicator is created; stdout carries the ONE JSON line of this
+        # run, so file descriptor 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            # short collective timeout: a rank that dies must not park its peers in a barrier for the default 10 minutes
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=args.nccl_timeout))
+            if local_rank == 0:                                     # one builder per node, then everybody loads the finished library
+                _libmod.load()
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     T, S = args.frames, args.phonemes
     B = args.batch if args.scaling == "weak" else max(1, args.batch // world)
     utt0 = rank * B

@@ -132,6 +132,12 @@ int tts_debug_phase_timestamps(TtsHandle* h, void* ws, unsigned long long* out, 
  * see decode_cluster.cuh: dbg_dump); this copies `n` floats starting at float `offset` of that dump to the host. [sync] */
 int tts_debug_read_dump(TtsHandle* h, void* ws, int64_t offset, int64_t n, float* out_host, void* stream);
 
+/* Layout of the decode kernel's K/V cache (host arithmetic only, no device work): element index (0 .. 8191) of K[row][dim]
+ * (which = 0) or V[row][dim] (which = 1) inside a 64-row cache block; row in [0, 64), dim in [0, 64).  -1 on bad arguments.
+ * The layout is part of the kernel contract (a ring stage must be one contiguous copy, a V fragment one 16-byte load), so the
+ * CPU test suite checks it without a GPU. */
+int tts_debug_kv_index(int row, int dim, int which);
+
 /* ---- training step (oracle: TransformerTTS.forward in .train() mode + tts_loss + autograd + torch.optim.Adam;
  *      oracle/transformer_tts.py:forward, :tts_loss, :masked_batchnorm) ---------------- */
 /* Build the training state from the weights loaded so far: one flat fp32 parameter buffer (+ gradients, Adam

@@ -74,3 +74,30 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_kv_cache_block_layout():
+    """The decode kernel's cache block layout (host arithmetic of the shipped library, no GPU): a bijection onto 8192 elements;
+    rows [0, 16 n) of K and V together fill exactly the first 16 n * 128 elements (so any ring stage is ONE contiguous copy);
+    K rows are row-major inside a 16-row sub-chunk; the V half of a sub-chunk is in mma.m16n8k16 A-fragment order of V^T."""
+    from transformer_tacotron2_b200 import _lib
+    lib = _lib.load()
+    idx = {(w, r, d): lib.tts_debug_kv_index(r, d, w) for w in (0, 1) for r in range(64) for d in range(64)}
+    assert sorted(idx.values()) == list(range(8192))
+    assert lib.tts_debug_kv_index(64, 0, 0) == -1 and lib.tts_debug_kv_index(0, 64, 1) == -1 and lib.tts_debug_kv_index(0, 0, 2) == -1
+    for n in range(1, 5):
+        got = sorted(v for (w, r, d), v in idx.items() if r < 16 * n)
+        assert got == list(range(16 * n * 128))
+    for r in range(64):
+        base = (r // 16) * 2048 + (r % 16) * 64
+        assert [idx[(0, r, d)] for d in range(64)] == list(range(base, base + 64))
+    for s in range(4):                     # 16-row sub-chunk
+        for dt in range(4):                # 16-dim tile of V^T
+            for g in range(8):
+                for t4 in range(4):
+                    base = s * 2048 + 1024 + (dt * 32 + g * 4 + t4) * 8
+                    want = [(16 * s + 4 * t4 + 0, 16 * dt + g), (16 * s + 4 * t4 + 1, 16 * dt + g),            # a0: A[g][2 t4, 2 t4 + 1]
+                            (16 * s + 4 * t4 + 0, 16 * dt + g + 8), (16 * s + 4 * t4 + 1, 16 * dt + g + 8),    # a1: A[g + 8][..]
+                            (16 * s + 4 * t4 + 2, 16 * dt + g), (16 * s + 4 * t4 + 3, 16 * dt + g),            # a2: A[g][2 t4 + 8, + 9]
+                            (16 * s + 4 * t4 + 2, 16 * dt + g + 8), (16 * s + 4 * t4 + 3, 16 * dt + g + 8)]    # a3
+                    assert [idx[(1, r, d)] for r, d in want] == list(range(base, base + 8))

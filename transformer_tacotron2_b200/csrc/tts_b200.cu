@@ -818,6 +818,11 @@ extern "C" int tts_debug_read_dump(TtsHandle* h, void* ws, int64_t offset, int64
     return 0;
 }
 
+extern "C" int tts_debug_kv_index(int row, int dim, int which) {
+    if (row < 0 || row >= KV_BLOCK_ROWS || dim < 0 || dim >= kDHead || which < 0 || which > 1) return -1;
+    return which ? kv_v_elem(row, dim) : kv_k_elem(row, dim);
+}
+
 // per-kernel test entry points
 extern "C" int tts_k_gemm(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int act, void* stream) {
     if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 128)) return TTS_E_ARG;

@@ -162,17 +162,17 @@ struct ClCtx {
 // ---------------------------------------------------------------- the stage stream of one step (shared by producer and consumers)
 // seg: 0 fc1, 1 fc2, 2 proj, 3+8l+{0 qkv, 1 self-KV, 2 o, 3 q2, 4 cross-KV, 5 o2, 6 w1, 7 w2}, 51 head.
 // A weight segment is `total` bytes for `na` warps, `bw` bytes each, 32768 / bw warps per stage.
-struct WSeg { int total, bw, na; };
+struct WSeg { int total, bw, na, nh; };             // nh: the K range of every warp is streamed in nh parts (1 or 2), part-major
 TTS_D WSeg wseg(int seg, int rank) {
-    if (seg == 0) return {CLW_FC1, 4096, 2};
-    if (seg == 1) return {CLW_FC2, 8192, 2};
-    if (seg == 2) return {CLW_PROJ, 8192, 4};
-    if (seg == 51) return {rank < 6 ? CLW_HEAD : 0, 16384, rank < 6 ? 1 : 0};
+    if (seg == 0) return {CLW_FC1, 4096, 2, 1};
+    if (seg == 1) return {CLW_FC2, 8192, 2, 1};
+    if (seg == 2) return {CLW_PROJ, 8192, 4, 1};
+    if (seg == 51) return {rank < 6 ? CLW_HEAD : 0, 16384, rank < 6 ? 1 : 0, 1};
     switch ((seg - 3) & 7) {
-    case 0: return {CLW_QKV, 16384, 12};
-    case 6: return {CLW_W1, 16384, 16};
-    case 7: return {CLW_W2, 16384, 16};
-    default: return {CLW_O, 16384, 4};
+    case 0: return {CLW_QKV, 8192, 12, 2};               // the wide GEMMs stream every warp's K range in two halves (cl_gemm<.., 2>)
+    case 6: return {CLW_W1, 8192, 16, 2};
+    case 7: return {CLW_W2, 8192, 16, 2};
+    default: return {CLW_O, 16384, 4, 1};
     }
 }
 
@@ -225,11 +225,12 @@ TTS_D void cl_producer(const ClusterParams& p, unsigned char* smem, uint64_t* fu
                     }
             } else {
                 const WSeg ws = wseg(seg, rank);
-                const int wps = CL_STAGE_BYTES / ws.bw;
-                for (int done = 0, w0 = 0; done < ws.total; done += CL_STAGE_BYTES, w0 += wps) {
+                const int wps = CL_STAGE_BYTES / ws.bw, part = ws.total / ws.nh;
+                for (int done = 0, w0 = 0; done < ws.total && !stopped; done += CL_STAGE_BYTES, w0 += wps) {
+                    if (done == part) w0 = 0;            // second half: the warps again, from warp 0 (a part is a whole number of stages)
                     uint32_t stage;
                     if (!slot(stage)) break;
-                    const uint32_t bytes = (uint32_t)min(CL_STAGE_BYTES, ws.total - done);
+                    const uint32_t bytes = (uint32_t)min(CL_STAGE_BYTES, (done < part ? part : ws.total) - done);
                     const int readers = min(wps, ws.na - w0);
                     mbar_expect_tx(fbar, bytes);
                     bulk_g2s(smem + SM_RING + stage * CL_STAGE_BYTES, wbase + woff, bytes, fbar, pol_w);
@@ -263,11 +264,15 @@ TTS_D void cl_release(const ClCtx& c, uint32_t idx) {
 // contiguous run of TW*KP KB ([kp][j] blocks of 1 KB) inside a ring stage shared with its neighbours; the accumulators never leave
 // registers (NCH independent MMA chains per tile).  epi(tile, n, m, value) receives complete sums (+ bias).  No block-level
 // barrier inside: callers synchronise where the results are consumed.
-template <int KP, int TW, class BiasFn, class Epi>
+template <int KP, int TW, int NH = 1, class BiasFn, class Epi>
 TTS_D void cl_gemm(ClCtx& c, int na, const bf16* X, int ldx, BiasFn biasf, Epi epi, unsigned long long* tstamp = nullptr) {
-    constexpr int BW = TW * KP * 1024, WPS = CL_STAGE_BYTES / BW;
+    // NH = 2: the warp's K range arrives in two halves, all warps' first halves first (BW bytes per warp and half, 32768 / BW
+    // warps per stage): a slot is handed back after half an MMA loop, so the stages beyond the ring's depth are re-issued (and
+    // land) while the first halves are still being multiplied.
+    constexpr int KH = KP / NH, BW = TW * KH * 1024, WPS = CL_STAGE_BYTES / BW;
     constexpr int NCH = (TW == 1 && KP >= 16) ? 4 : 2;
-    const int nst = (na + WPS - 1) / WPS;
+    static_assert(KH % 4 == 0, "k-steps per part must be a multiple of the unroll factor");
+    const int nst = (na + WPS - 1) / WPS;                // stages per part
     if (c.warp < na) {
         const int g = c.lane >> 2, t4 = c.lane & 3;
         float bias[TW][2];
@@ -278,30 +283,36 @@ TTS_D void cl_gemm(ClCtx& c, int na, const bf16* X, int ldx, BiasFn biasf, Epi e
         for (int j = 0; j < TW; ++j)
 #pragma unroll
             for (int q = 0; q < NCH; ++q) { acc[j][q][0] = acc[j][q][1] = acc[j][q][2] = acc[j][q][3] = 0.f; }
-        const uint32_t idx = c.consumed + (uint32_t)(c.warp / WPS);
-        if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory"); tstamp[0] = now; }
-        const uint4* wp = reinterpret_cast<const uint4*>(cl_acquire(c, idx) + (c.warp % WPS) * BW);
-        if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "l"(wp) : "memory"); tstamp[1] = now; }
         const bf16* xrow = X + (c.lane & 7) * ldx + (c.lane >> 3) * 8;
 #pragma unroll 1
-        for (int kq = 0; kq < KP / 4; ++kq) {            // four k-steps per iteration: a fully unrolled K loop in every GEMM makes
+        for (int h = 0; h < NH; ++h) {
+            const uint32_t idx = c.consumed + (uint32_t)(h * nst + c.warp / WPS);
+            if (tstamp && h == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory"); tstamp[0] = now; }
+            const uint4* wp = reinterpret_cast<const uint4*>(cl_acquire(c, idx) + (c.warp % WPS) * BW);
+            if (tstamp && h == 0) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "l"(wp) : "memory"); tstamp[1] = now; }
+#pragma unroll 1
+            for (int kq = 0; kq < KH / 4; ++kq) {        // four k-steps per iteration: a fully unrolled K loop in every GEMM makes
 #pragma unroll                                           // the kernel too large for the instruction cache
-            for (int ku = 0; ku < 4; ++ku) {
-                const int kp = kq * 4 + ku;
-                uint32_t bfrag[4];
-                ldmatrix_x4(bfrag, xrow + kp * 32);
+                for (int ku = 0; ku < 4; ++ku) {
+                    const int kl = kq * 4 + ku;          // k-pair inside this part
+                    uint32_t bfrag[4];
+                    ldmatrix_x4(bfrag, xrow + (h * KH + kl) * 32);
 #pragma unroll
-                for (int j = 0; j < TW; ++j) {
-                    const uint4 w0 = wp[((kp * TW + j) * 2) * 32 + c.lane];
-                    const uint4 w1 = wp[((kp * TW + j) * 2 + 1) * 32 + c.lane];
-                    const uint32_t a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w};
-                    mma_bf16_16816(acc[j][ku % NCH], a0, bfrag[0], bfrag[1]);
-                    mma_bf16_16816(acc[j][ku % NCH], a1, bfrag[2], bfrag[3]);
+                    for (int j = 0; j < TW; ++j) {
+                        const uint4 w0 = wp[((kl * TW + j) * 2) * 32 + c.lane];
+                        const uint4 w1 = wp[((kl * TW + j) * 2 + 1) * 32 + c.lane];
+                        const uint32_t a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w};
+                        mma_bf16_16816(acc[j][ku % NCH], a0, bfrag[0], bfrag[1]);
+                        mma_bf16_16816(acc[j][ku % NCH], a1, bfrag[2], bfrag[3]);
+                    }
                 }
             }
+            if (h + 1 < NH) cl_release(c, idx);
+            else {
+                if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(acc[0][0][0]), "f"(acc[TW - 1][NCH - 1][3]) : "memory"); tstamp[2] = now; }
+                cl_release(c, idx);
+            }
         }
-        if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(acc[0][0][0]), "f"(acc[TW - 1][NCH - 1][3]) : "memory"); tstamp[2] = now; }
-        cl_release(c, idx);
         const int m0 = t4 * 2;
 #pragma unroll
         for (int j = 0; j < TW; ++j) {
@@ -318,7 +329,7 @@ TTS_D void cl_gemm(ClCtx& c, int na, const bf16* X, int ldx, BiasFn biasf, Epi e
             if (m0 + 1 < c.G) { epi(tile, g, m0 + 1, s[1] + bias[j][0]); epi(tile, g + 8, m0 + 1, s[3] + bias[j][1]); }
         }
     }
-    c.consumed += (uint32_t)nst;
+    c.consumed += (uint32_t)(NH * nst);
 }
 
 // ---- DSMEM pushes that carry their own completion ---------------------------------------------------------------
@@ -746,7 +757,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                 for (int l = 0; l < 6; ++l) {
                     const ClusterLayerParams& W = p.layer[l];
                     // ---- q, k, v of head `rank` for every row of the group (local; k_t, v_t appended to the cache)
-                    cl_gemm<16, 1>(c, 12, xa, LDX512,
+                    cl_gemm<16, 1, 2>(c, 12, xa, LDX512,
                             [&](int ti, int n) { const int cc = ti * 16 + n; return __ldg(W.bqkv + (cc >> 6) * 512 + c.rank * 64 + (cc & 63)); },
                             [&](int ti, int n, int m, float v) {
                                 const int cc = ti * 16 + n, part = cc >> 6, dd = cc & 63;
@@ -799,7 +810,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     stamp(t, 8 + 8 * l);
                     if (l == 0) dbg_dump(t, 5, xa, LDX512, 512, true);
                     // ---- FFN: hidden slice [256 rank, +256) stays local (bf16); FFN2 is split along K
-                    cl_gemm<16, 1>(c, 16, xa, LDX512,
+                    cl_gemm<16, 1, 2>(c, 16, xa, LDX512,
                             [&](int ti, int n) { return __ldg(W.b1 + c.rank * 256 + ti * 16 + n); },
                             [&](int ti, int n, int m, float v) { hbuf[m * LDX256 + ti * 16 + n] = __float2bfloat16(fmaxf(v, 0.f)); },
                             (stamper && l == 0) ? p.ts + (size_t)t * CL_TS_COLS + 76 : nullptr);
@@ -808,7 +819,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     if (l == 0) dbg_dump(t, 6, hbuf, LDX256, 256, true);
                     // partial sums over this rank's 256 hidden units, staged in ybuf (free between LN2 and the y3 gather)
                     ln_prefetch(c, W.ln3g, W.ln3b);
-                    cl_gemm<8, 2>(c, 16, hbuf, LDX256, [&](int, int) { return 0.f; },
+                    cl_gemm<8, 2, 2>(c, 16, hbuf, LDX256, [&](int, int) { return 0.f; },
                             [&](int ti, int n, int m, float v) { ybuf[m * 512 + ti * 16 + n] = v; },
                             (stamper && l == 0) ? p.ts + (size_t)t * CL_TS_COLS + 79 : nullptr);
                     if (l == 0) stamp(t, 55);

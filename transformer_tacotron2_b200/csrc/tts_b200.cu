@@ -374,12 +374,15 @@ extern "C" int tts_finalize_weights(TtsHandle* h) {
                 GET(w1, p + ".ffn.w1.weight", (size_t)F * D); GET(w2, p + ".ffn.w2.weight", (size_t)D * F);
                 std::vector<int> qrows(192);                      // q, k, v (64 dims each) of head rk
                 for (int cc = 0; cc < 192; ++cc) qrows[cc] = (cc >> 6) * 512 + rk * 64 + (cc & 63);
-                pack_cluster_segment(seg, w3.data(), 3 * D, D, qrows, 0, 16, 1);
+                pack_cluster_segment(seg, w3.data(), 3 * D, D, qrows, 0, 8, 1);                // wide GEMMs: K in two halves, all warps'
+                pack_cluster_segment(seg, w3.data(), 3 * D, D, qrows, 8, 8, 1);                // first halves first (cl_gemm<.., 2>)
                 pack_cluster_segment(seg, wo, D, D, iota_rows(64 * rk, 64), 0, 16, 1);
                 pack_cluster_segment(seg, wq2, D, D, iota_rows(64 * rk, 64), 0, 16, 1);
                 pack_cluster_segment(seg, wo2, D, D, iota_rows(64 * rk, 64), 0, 16, 1);
-                pack_cluster_segment(seg, w1, F, D, iota_rows(256 * rk, 256), 0, 16, 1);
-                pack_cluster_segment(seg, w2, D, F, iota_rows(0, 512), 8 * rk, 8, 2);          // K-slice [256 rk, 256 rk + 256), two tiles per warp
+                pack_cluster_segment(seg, w1, F, D, iota_rows(256 * rk, 256), 0, 8, 1);
+                pack_cluster_segment(seg, w1, F, D, iota_rows(256 * rk, 256), 8, 8, 1);
+                pack_cluster_segment(seg, w2, D, F, iota_rows(0, 512), 8 * rk, 4, 2);          // K-slice [256 rk, 256 rk + 256), two tiles per warp
+                pack_cluster_segment(seg, w2, D, F, iota_rows(0, 512), 8 * rk + 4, 4, 2);
             }
             std::vector<int> hrows(16);
             for (int i = 0; i < 16; ++i) hrows[i] = (rk < 6 && 16 * rk + i < 81) ? 16 * rk + i : -1;

@@ -564,7 +564,8 @@ TTS_D void cl_attention(const ClusterParams& p, ClCtx& c, bool self, int t, cons
     }
     c.consumed += (uint32_t)(nj * c.G);
     if (stamp_row) stamp_row[self ? 61 : 64] = timer_after_lds(c.smem + SM_MISC + 192);
-    consumer_bar();
+    // the pair's three warps only (named barrier 2 + gi): a pair that is done merges and pushes while the others still stream
+    if (active) asm volatile("bar.sync %0, 96;" ::"r"(2 + gi) : "memory");
     if (stamp_row) stamp_row[self ? 62 : 65] = timer_after_lds(c.smem + SM_MISC + 192);
     if (active && wv == 0) {                             // merge the pair's three partials (+ the newest row) in fixed order
         const float* pa = part;

@@ -164,6 +164,7 @@ struct ClCtx {
 // A weight segment is `total` bytes for `na` warps, `bw` bytes each, 32768 / bw warps per stage.
 struct WSeg { int total, bw, na, nh; };             // nh: the K range of every warp is streamed in nh parts (1 or 2), part-major
 TTS_D WSeg wseg(int seg, int rank) {
+    // (prenet and heads stay on one warp per tile: spreading these tiny GEMMs over K parts measured slower)
     if (seg == 0) return {CLW_FC1, 4096, 2, 1};
     if (seg == 1) return {CLW_FC2, 8192, 2, 1};
     if (seg == 2) return {CLW_PROJ, 8192, 4, 1};
@@ -332,52 +333,60 @@ TTS_D void cl_gemm(ClCtx& c, int na, const bf16* X, int ldx, BiasFn biasf, Epi e
     c.consumed += (uint32_t)(NH * nst);
 }
 
-// The narrow GEMMs (64 output columns of this rank, K = 512: O, cross-Q, O2) on all 16 warps: warp w multiplies K quarter
-// w >> 2 of tile w & 3 (a 4 KB piece of the tile's contiguous 16 KB run -- no repacking), quarters 1..3 park their sums in
-// shared memory, the tile's four warps meet at a named barrier and warp `tile` (quarter 0) adds them in fixed order and runs
-// the epilogue.  With 4 warps the MMA loop was a 32-deep dependent chain per warp (0.5 us); now it is 8 MMAs per warp.
-template <class BiasFn, class Epi>
+// The narrow GEMMs of a layer (NT <= 4 output tiles of this rank: O, cross-Q, O2) spread over NT x NQ warps: warp w multiplies
+// K part w / NT of tile w % NT (a piece of the tile's contiguous run -- no repacking), parts 1.. park their sums in shared
+// memory, the tile's NQ warps meet at a named barrier and warp `tile` (part 0) adds them in fixed order and runs the epilogue.
+// With one warp per tile the MMA loop was a 2 KP-deep dependent chain (0.5 us for K = 512); now it is 2 KP / NQ MMAs per warp.
+template <int NT, int KP, int NQ, class BiasFn, class Epi>
 TTS_D void cl_gemm_ksplit(ClCtx& c, const bf16* X, int ldx, BiasFn biasf, Epi epi, unsigned long long* tstamp = nullptr) {
-    const int tile = c.warp & 3, kq = c.warp >> 2, run = tile * 4 + kq;
-    const int g = c.lane >> 2, t4 = c.lane & 3;
-    float bias0 = 0.f, bias1 = 0.f;
-    if (kq == 0) { bias0 = biasf(tile, g); bias1 = biasf(tile, g + 8); }
-    float acc[4][4];
+    constexpr int KQ = KP / NQ, RUN = KQ * 1024, RPS = CL_STAGE_BYTES / RUN;     // k-pairs per warp, bytes per warp, warps per stage
+    static_assert(KQ >= 1 && KQ <= 4 && NT * NQ <= CL_WARPS && NQ <= 4, "cl_gemm_ksplit geometry");
+    constexpr int NST = (NT * KP * 1024 + CL_STAGE_BYTES - 1) / CL_STAGE_BYTES;
+    if (c.warp < NT * NQ) {
+        const int tile = c.warp % NT, kq = c.warp / NT, run = tile * NQ + kq;
+        const int g = c.lane >> 2, t4 = c.lane & 3;
+        float bias0 = 0.f, bias1 = 0.f;
+        if (kq == 0) { bias0 = biasf(tile, g); bias1 = biasf(tile, g + 8); }
+        float acc[KQ][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f; }
-    const uint32_t idx = c.consumed + (uint32_t)(run >> 3);
-    if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory"); tstamp[0] = now; }
-    const uint4* wp = reinterpret_cast<const uint4*>(cl_acquire(c, idx) + (run & 7) * 4096);
-    if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "l"(wp) : "memory"); tstamp[1] = now; }
-    const bf16* xrow = X + (c.lane & 7) * ldx + (c.lane >> 3) * 8 + kq * 128;
+        for (int q = 0; q < KQ; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f; }
+        const uint32_t idx = c.consumed + (uint32_t)(run / RPS);
+        if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) :: "memory"); tstamp[0] = now; }
+        const uint4* wp = reinterpret_cast<const uint4*>(cl_acquire(c, idx) + (run % RPS) * RUN);
+        if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "l"(wp) : "memory"); tstamp[1] = now; }
+        const bf16* xrow = X + (c.lane & 7) * ldx + (c.lane >> 3) * 8 + kq * KQ * 32;
 #pragma unroll
-    for (int ku = 0; ku < 4; ++ku) {
-        uint32_t bfrag[4];
-        ldmatrix_x4(bfrag, xrow + ku * 32);
-        const uint4 w0 = wp[(ku * 2) * 32 + c.lane];
-        const uint4 w1 = wp[(ku * 2 + 1) * 32 + c.lane];
-        const uint32_t a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w};
-        mma_bf16_16816(acc[ku], a0, bfrag[0], bfrag[1]);
-        mma_bf16_16816(acc[ku], a1, bfrag[2], bfrag[3]);
-    }
-    if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(acc[0][0]), "f"(acc[3][3]) : "memory"); tstamp[2] = now; }
-    cl_release(c, idx);
-    float4 sum = make_float4((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]), (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]),
-                             (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]), (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]));
-    float4* part = reinterpret_cast<float4*>(c.smem + SM_RECV);           // [3 quarters][4 tiles][32 lanes]; idle outside the FFN2 reduce-scatter
-    if (kq > 0) part[((kq - 1) * 4 + tile) * 32 + c.lane] = sum;
-    asm volatile("bar.sync %0, 128;" ::"r"(8 + tile) : "memory");        // the four warps of the tile
-    if (kq == 0) {
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {                                     // fixed order: deterministic
-            const float4 o = part[(q * 4 + tile) * 32 + c.lane];
-            sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+        for (int ku = 0; ku < KQ; ++ku) {
+            uint32_t bfrag[4];
+            ldmatrix_x4(bfrag, xrow + ku * 32);
+            const uint4 w0 = wp[(ku * 2) * 32 + c.lane];
+            const uint4 w1 = wp[(ku * 2 + 1) * 32 + c.lane];
+            const uint32_t a0[4] = {w0.x, w0.y, w0.z, w0.w}, a1[4] = {w1.x, w1.y, w1.z, w1.w};
+            mma_bf16_16816(acc[ku], a0, bfrag[0], bfrag[1]);
+            mma_bf16_16816(acc[ku], a1, bfrag[2], bfrag[3]);
         }
-        const int m0 = t4 * 2;
-        if (m0 < c.G) { epi(tile, g, m0, sum.x + bias0); epi(tile, g + 8, m0, sum.z + bias1); }
-        if (m0 + 1 < c.G) { epi(tile, g, m0 + 1, sum.y + bias0); epi(tile, g + 8, m0 + 1, sum.w + bias1); }
+        if (tstamp) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now) : "f"(acc[0][0]), "f"(acc[KQ - 1][3]) : "memory"); tstamp[2] = now; }
+        cl_release(c, idx);
+        float4 sum = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+#pragma unroll
+        for (int q = 1; q < KQ; ++q) { sum.x += acc[q][0]; sum.y += acc[q][1]; sum.z += acc[q][2]; sum.w += acc[q][3]; }    // fixed order
+        float4* part = reinterpret_cast<float4*>(c.smem + SM_RECV);       // [NQ - 1][NT][32 lanes]; idle outside the FFN2 reduce-scatter
+        if (NQ > 1) {
+            if (kq > 0) part[((kq - 1) * NT + tile) * 32 + c.lane] = sum;
+            asm volatile("bar.sync %0, %1;" ::"r"(8 + tile), "n"(NQ * 32) : "memory");      // the NQ warps of the tile
+        }
+        if (kq == 0) {
+#pragma unroll
+            for (int q = 0; q < NQ - 1; ++q) {                            // fixed order: deterministic
+                const float4 o = part[(q * NT + tile) * 32 + c.lane];
+                sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+            }
+            const int m0 = t4 * 2;
+            if (m0 < c.G) { epi(tile, g, m0, sum.x + bias0); epi(tile, g + 8, m0, sum.z + bias1); }
+            if (m0 + 1 < c.G) { epi(tile, g, m0 + 1, sum.y + bias0); epi(tile, g + 8, m0 + 1, sum.w + bias1); }
+        }
     }
-    c.consumed += 2u;
+    c.consumed += (uint32_t)NST;
 }
 
 // ---- DSMEM pushes that carry their own completion ---------------------------------------------------------------
@@ -825,7 +834,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     if (l == 0) dbg_dump(t, 2, abuf, LDX512, 512, true);
                     // ---- O projection + residual, gathered -> LayerNorm 1
                     ln_prefetch(c, W.ln1g, W.ln1b);
-                    cl_gemm_ksplit(c, abuf, LDX512,
+                    cl_gemm_ksplit<4, 16, 4>(c, abuf, LDX512,
                             [&](int ti, int n) { return __ldg(W.bo + c.rank * CL_NS + ti * 16 + n); },
                             [&](int ti, int n, int m, float v) { wst[m * 16 + n] = v + xres[m * 512 + c.rank * CL_NS + ti * 16 + n]; },
                             (stamper && l == 0) ? p.ts + (size_t)t * CL_TS_COLS + 73 : nullptr);
@@ -839,7 +848,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     stamp(t, 5 + 8 * l);
                     if (l == 0) dbg_dump(t, 3, xa, LDX512, 512, true);
                     // ---- cross-attention query of head `rank` (local)
-                    cl_gemm_ksplit(c, xa, LDX512,
+                    cl_gemm_ksplit<4, 16, 4>(c, xa, LDX512,
                             [&](int ti, int n) { return __ldg(W.bq2 + c.rank * CL_NS + ti * 16 + n); },
                             [&](int ti, int n, int m, float v) { qkvb[m * 192 + ti * 16 + n] = v; });
                     consumer_bar();
@@ -849,7 +858,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) decode_cluster_kernel(const __g
                     stamp(t, 7 + 8 * l);
                     if (l == 0) dbg_dump(t, 4, abuf, LDX512, 512, true);
                     ln_prefetch(c, W.ln2g, W.ln2b);
-                    cl_gemm_ksplit(c, abuf, LDX512,
+                    cl_gemm_ksplit<4, 16, 4>(c, abuf, LDX512,
                             [&](int ti, int n) { return __ldg(W.bo2 + c.rank * CL_NS + ti * 16 + n); },
                             [&](int ti, int n, int m, float v) { wst[m * 16 + n] = v + xres[m * 512 + c.rank * CL_NS + ti * 16 + n]; });
                     if (c.warp < 4) { __syncwarp(); push_tile_f32(c, wst, ybuf + c.rank * CL_NS + c.warp * 16, 512); }

@@ -14,17 +14,19 @@
 // when one lane runs the loop alone, ~0.35 us when a whole warp loops; a consumer warp ~0.28 us per wait -> release round),
 // not by bytes.  So:
 //   * the producer is ONE elected lane;
-//   * a stage is read only by the warps that own its contents.  GEMMs: warp w owns output tile(s) w over the WHOLE local
-//     K; its weights are one contiguous run (16 KB for K = 512) and a 32 KB stage carries the runs of consecutive warps
-//     -- a warp waits ONCE per GEMM and no K-split reduction through shared memory exists any more.  Attention: a stage
-//     is 128 cache rows of ONE (utterance, head) pair, read by that pair's 3 warps;
-//   * the K/V cache is laid out in 64-row blocks with K and V interleaved, so 128 rows of a pair are ONE 32 KB copy
-//     (the copy engine needs ~44 ns per separate piece: the round-1 chunk of 2 x G pieces of 2 KB ran at 41 GB/s per SM).
+//   * a stage is read only by the warps that own its contents.  Wide GEMMs (QKV, FFN1, FFN2): warp w owns output tile(s) w
+//     over the whole local K; its weights are contiguous runs, streamed in two K halves (all warps' first halves first, so
+//     that slots are handed back after half an MMA loop).  Narrow GEMMs (O, cross-Q, O2: four tiles per rank): 4 tiles x 4
+//     K quarters on all 16 warps, the quarters summed in fixed order through shared memory (cl_gemm_ksplit) -- with one
+//     warp per tile the MMA loop is a long dependent chain.  Attention: a stage is up to 128 cache rows of ONE
+//     (utterance, head) pair, read by that pair's 3 warps, one online-softmax round per warp and stage;
+//   * every stage is ONE bulk copy (the copy engine needs ~44 ns per separate piece: the round-1 K/V chunk of 2 x G pieces
+//     of 2 KB ran at 41 GB/s per SM).
 //
-// KV-cache layout (P18, adapted): per (layer, utterance, head) a run of 64-row blocks, 16 KB each:
-//     [ K rows 0..63 row-major [64][64] bf16 | V in four 16-row sub-blocks, each stored transposed [64 d][16 rows] ]
-// Both halves are A operands of mma.sync.m16n8k16 straight from shared memory with conflict-free 16- / 8-byte loads
-// (the k index of an MMA may be permuted freely as long as A and B agree).
+// KV-cache layout (P18, adapted; kv_k_elem / kv_v_elem in common.cuh): per (layer, utterance, head) a run of 64-row blocks of
+// 16 KB = four 16-row sub-chunks [ K 16 rows row-major [16][64] bf16 | V 16 rows in mma.m16n8k16 A-fragment order of V^T ].
+// Rows [0, 16 n) of a pair are one contiguous range.  K rows are the B operand of the score MMAs (A = q), V fragments the A
+// operand of the output MMAs (B = p): the probabilities go from the score registers straight into the next MMA.
 // Weights are packed per CTA rank in exactly the order the step consumes them (tts_b200.cu: pack_cluster_segment), each
 // 16(n) x 32(k) block in A-fragment order.
 #pragma once

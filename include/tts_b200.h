@@ -137,6 +137,13 @@ int tts_debug_read_dump(TtsHandle* h, void* ws, int64_t offset, int64_t n, float
  * The layout is part of the kernel contract (a ring stage must be one contiguous copy, a V fragment one 16-byte load), so the
  * CPU test suite checks it without a GPU. */
 int tts_debug_kv_index(int row, int dim, int which);
+/* The decode kernel's weight stream (host arithmetic only): packs rows `rows[0 .. nrows)` (nrows a multiple of 16 * TW; -1 = zero
+ * row) x k-pairs [kp_base, kp_base + KP) (32 columns each) of the fp32 matrix w[N][K] exactly as tts_finalize_weights does for one
+ * segment of one rank -- per warp a contiguous run of [k-pair][tile] blocks of 1 KB in mma.m16n8k16 A-fragment order, bf16.
+ * Writes nrows / 16 * KP KB to `out` (returns the byte count, or the count needed if out is NULL / too small; -1 on bad
+ * arguments).  The CPU tests re-read the stream with the kernel's addressing. */
+int64_t tts_debug_pack_segment(const float* w, int N, int K, const int32_t* rows, int nrows, int kp_base, int KP, int TW,
+                               unsigned char* out, int64_t out_bytes);
 
 /* ---- training step (oracle: TransformerTTS.forward in .train() mode + tts_loss + autograd + torch.optim.Adam;
  *      oracle/transformer_tts.py:forward, :tts_loss, :masked_batchnorm) ---------------- */

@@ -44,6 +44,7 @@ SIGNATURES = {
     "tts_debug_phase_timestamps": (_I, [_P, _P, _P, _I, _P]),
     "tts_debug_read_dump": (_I, [_P, _P, _I64, _I64, _P, _P]),
     "tts_debug_kv_index": (_I, [_I, _I, _I]),
+    "tts_debug_pack_segment": (_I64, [_P, _I, _I, _P, _I, _I, _I, _I, _P, _I64]),
     "tts_train_begin": (_I, [_P]),
     "tts_train_end": (_I, [_P]),
     "tts_train_workspace_bytes": (_SZ, [_P, _I, _I, _I]),

@@ -826,6 +826,18 @@ extern "C" int tts_debug_kv_index(int row, int dim, int which) {
     return which ? kv_v_elem(row, dim) : kv_k_elem(row, dim);
 }
 
+extern "C" int64_t tts_debug_pack_segment(const float* w, int N, int K, const int32_t* rows, int nrows, int kp_base, int KP, int TW,
+                                          unsigned char* out, int64_t out_bytes) {
+    if (!w || !rows || N <= 0 || K <= 0 || nrows <= 0 || KP <= 0 || kp_base < 0 || TW <= 0 || nrows % (16 * TW) != 0) return -1;
+    const int64_t need = (int64_t)(nrows / 16) * KP * 1024;
+    if (!out || out_bytes < need) return need;
+    std::vector<unsigned char> seg;
+    seg.reserve((size_t)need);
+    pack_cluster_segment(seg, w, N, K, std::vector<int>(rows, rows + nrows), kp_base, KP, TW);
+    memcpy(out, seg.data(), seg.size());
+    return (int64_t)seg.size();
+}
+
 // per-kernel test entry points
 extern "C" int tts_k_gemm(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int act, void* stream) {
     if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 128)) return TTS_E_ARG;
